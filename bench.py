@@ -1,0 +1,351 @@
+#!/usr/bin/env python
+"""bench.py -- headline benchmark of pdgn_b200: all-pairs Chamfer-distance matrix throughput.
+
+  python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference]
+  python -m torch.distributed.run --nnodes=1 --nproc-per-node N --master-addr 127.0.0.1 --master-port P bench.py --gpus N ...
+
+Workload (BASELINE.json configs[3], the configuration the metric "CD pairs/s" is quoted on; it fits one GPU):
+1000 generated x 1000 reference synthetic clouds of 2048 points (S: unit sphere + N(0,0.01^2) radial noise, seeds 0/1).
+One step = the whole 1000x1000 matrix (10^6 cloud pairs, 4.19e12 point-pair distances).  With N ranks the pair grid
+is 2-D tiled (pdgn_b200.dist) and the per-pair scalars are all-gathered over NCCL inside the step => strong scaling.
+
+One JSON line on rank 0:
+  value          cloud pairs/s, device-resident inputs, CUDA events on the launch stream, max over ranks
+  e2e            same metric through the public API (_pairwise_EMD_CD_) from pinned HOST tensors, H2D + D2H inside
+  roofline       FP32-SIMT roofline of the dominant kernel (cd_allpairs_kernel): 6 FMA-pipe instructions per point pair
+  cpu_baseline   the reference's CPU formulation (oracle.torch_ref.pairwise_cd = distChamfer loop) on a bounded sample
+  knnquery       secondary metric of BASELINE.json (Mqueries/s, k=20, B=35 x 2048) measured in the same run
+`--impl reference` times only the CPU formulation (rank 0; other ranks exit 0).
+"""
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+N_CLOUDS = 1000
+N_PTS = 2048
+POINT_PAIRS_PER_CLOUD_PAIR = N_PTS * N_PTS
+FMA_PIPE_INSTR_PER_POINT_PAIR = 6   # 3 FADD + 1 FMUL + 2 FFMA
+FLOP_PER_POINT_PAIR = 8
+METRIC = "cd_cloud_pairs_per_s"
+UNIT = "cloud-pairs/s"
+WORKLOAD = "allpairs_cd_1000x1000_clouds_2048pts"
+
+
+def make_clouds(seed, n=N_CLOUDS, npts=N_PTS):
+    import numpy as np
+    import torch
+    rng = np.random.default_rng(seed)
+    v = rng.standard_normal(size=(n, npts, 3))
+    v /= np.linalg.norm(v, axis=-1, keepdims=True)
+    v *= 1.0 + 0.01 * rng.standard_normal(size=(n, npts, 1))
+    return torch.from_numpy(v.astype(np.float32))
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons DURING the timed region (B200_PROFILING.md recipe)."""
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.index, self.proc = index, None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q, "--format=csv,noheader,nounits",
+                                          "-lms", "100"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+        except OSError:
+            self.proc = None
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        try:
+            out, _ = self.proc.communicate(timeout=5)
+        except subprocess.TimeoutExpired:
+            self.proc.kill()
+            out, _ = self.proc.communicate()
+        sm, mx, pw, reasons = [], [], [], set()
+        for line in out.splitlines():
+            f = [x.strip() for x in line.split(",")]
+            if len(f) < 9:
+                continue
+            try:
+                sm.append(float(f[1])); mx.append(float(f[2])); pw.append(float(f[3]))
+            except ValueError:
+                continue
+            for name, val in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), f[5:9]):
+                if val.lower().startswith("active"):
+                    reasons.add(name)
+        if not sm:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["no samples"]}
+        return {"sm_mhz": statistics.median(sm), "sm_max_mhz": max(mx), "power_w_max": max(pw), "samples": len(sm),
+                "reasons": sorted(reasons)}
+
+
+def cpu_reference_rate(n_sample, n_ref, repeats=1):
+    """Reference CPU formulation (evaluation_metrics.py:85-121 / :35-45 restated in oracle.torch_ref) on a bounded
+    sample of the workload: n_sample x n_ref cloud pairs of 2048 points, batch_size 50 as in the README's test."""
+    import torch
+    from oracle import torch_ref
+    torch.set_num_threads(os.cpu_count() or 1)
+    smp = make_clouds(0, n_sample)
+    ref = make_clouds(1, n_ref)
+    torch_ref.pairwise_cd(smp[:1], ref[: min(n_ref, 10)], 50)  # warm-up (MKL init, page-in)
+    t0 = time.perf_counter()
+    for _ in range(repeats):
+        torch_ref.pairwise_cd(smp, ref, 50)
+    dt = (time.perf_counter() - t0) / repeats
+    return n_sample * n_ref / dt, dt
+
+
+def run_reference(args, rank):
+    """--impl reference: the reference's CPU path on the host cores (rank 0 only)."""
+    if rank != 0:
+        return
+    n_s, n_r = 2, 50  # 100 cloud pairs per step (~3 s on 8 cores): bounded sample of the 1000x1000 workload
+    for _ in range(args.warmup):
+        cpu_reference_rate(1, 10)
+    rates, times = [], []
+    for _ in range(args.steps):
+        r, dt = cpu_reference_rate(n_s, n_r)
+        rates.append(r); times.append(dt)
+    value = n_s * n_r * args.steps / sum(times)
+    cores = os.cpu_count() or 1
+    sample = "%d x %d cloud pairs of 2048 points per step (of the 1000 x 1000 workload), batch_size 50" % (n_s, n_r)
+    line = {
+        "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": 1e3 * sum(times) / args.steps, "higher_is_better": True, "scaling": "strong",
+        "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": WORKLOAD, "note": "reference CPU formulation (torch bmm Gram form + min, distChamfer loop) restated in "
+                   "oracle/torch_ref.py and pinned bit-exactly to the reference's own code by tests/golden; the Python reference itself "
+                   "cannot travel to the GPU box"},
+        "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
+        "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line), flush=True)
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--clouds", type=int, default=N_CLOUDS, help="debug: smaller matrix (the reported workload is 1000)")
+    ap.add_argument("--no-extras", action="store_true", help="skip the knnquery / gather / cpu_baseline side measurements")
+    args = ap.parse_args()
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+
+    if args.impl == "reference":
+        run_reference(args, rank)
+        return
+
+    import torch
+    import torch.distributed as dist
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device: the product path has no CPU fallback")
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    from pdgn_b200 import _build
+    if rank == 0:
+        _build.build()
+    if world > 1:
+        dist.barrier()
+    from pdgn_b200 import dist as pdist
+    from pdgn_b200 import evaluation_metrics as em
+    from pdgn_b200 import ops
+
+    nc = args.clouds
+    smp_h = make_clouds(0, nc).pin_memory()
+    ref_h = make_clouds(1, nc).pin_memory()
+    smp_d, ref_d = smp_h.to(dev), ref_h.to(dev)
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)  # > 126 MB L2
+
+    def step_device():
+        all_cd, _ = em._pairwise_EMD_CD_(smp_d, ref_d, 50)
+        return all_cd
+
+    def step_e2e():
+        a = smp_h.to(dev, non_blocking=True)
+        b = ref_h.to(dev, non_blocking=True)
+        all_cd, _ = em._pairwise_EMD_CD_(a, b, 50)
+        return all_cd.cpu()  # D2H of the step's result (synchronises)
+
+    def sync_all():
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+            torch.cuda.synchronize()
+
+    def timed(step, k):
+        """K steps bracketed by barrier + synchronize; CUDA events on the launch stream; max over ranks."""
+        sync_all()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(k):
+            flush.zero_()
+            out = step()
+        e1.record()
+        sync_all()
+        ms = torch.tensor([e0.elapsed_time(e1)], device=dev)
+        if world > 1:
+            dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+        return ms.item(), out
+
+    for _ in range(args.warmup):
+        step_device()
+    sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()
+    ms_total, out = timed(step_device, args.steps)
+    clocks = sampler.stop() if rank == 0 else None
+    for _ in range(min(args.warmup, 2)):
+        step_e2e()
+    ms_e2e, out_e2e = timed(step_e2e, args.steps)
+
+    # the dominant kernel alone (rank's own tile, no collective): CUDA events around the C-ABI launch.  The two pack
+    # kernels in the same call are ~0.01 % of it (profiles/: launch list).
+    rows, cols = pdist.tile_of(rank, world, nc, nc)
+    tile_pairs = (rows[1] - rows[0]) * (cols[1] - cols[0])
+    sync_all()
+    k0, k1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    kreps = max(1, min(args.steps, 3))
+    k0.record()
+    for _ in range(kreps):
+        ops.cd_allpairs(smp_d, ref_d, rows=rows, cols=cols)
+    k1.record()
+    torch.cuda.synchronize()
+    kernel_ms = k0.elapsed_time(k1) / kreps
+
+    if rank != 0:
+        if world > 1:
+            dist.barrier()
+            dist.destroy_process_group()
+        return
+
+    pairs = float(nc) * nc
+    value = pairs * args.steps / (ms_total * 1e-3)
+    e2e_value = pairs * args.steps / (ms_e2e * 1e-3)
+    props = torch.cuda.get_device_properties(dev)
+    peaks = {}
+    try:
+        peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+    except (OSError, ValueError):
+        pass
+    sm_max_mhz = float(peaks.get("sm_max_mhz") or (clocks or {}).get("sm_max_mhz") or 1965.0)
+    lanes = props.multi_processor_count * 128
+    peak_tflops = 2.0 * lanes * sm_max_mhz * 1e6 / 1e12           # FP32 FMA peak at max boost
+    inst_rate = tile_pairs * POINT_PAIRS_PER_CLOUD_PAIR * FMA_PIPE_INSTR_PER_POINT_PAIR / (kernel_ms * 1e-3)
+    achieved_tflops = 2.0 * inst_rate / 1e12                      # each FMA-pipe instruction = one FMA slot (2 FLOP)
+    obs_mhz = (clocks or {}).get("sm_mhz") or sm_max_mhz
+    roofline = {
+        "bound": "fp32", "kernel": "cd_allpairs_kernel", "achieved": achieved_tflops, "peak": peak_tflops, "unit": "TFLOP/s",
+        "frac": achieved_tflops / peak_tflops, "traffic": None,
+        "kernel_ms": kernel_ms, "cloud_pairs_per_launch": tile_pairs,
+        "definition": "achieved = cloud pairs x 2048^2 point pairs x 6 FMA-pipe instr x 2 FLOP-slots / kernel time (issue-rate "
+                      "fraction == FMA-pipe utilisation, SURVEY.md 8d); peak = SMs x 128 lanes x 2 x sm_max_mhz (MEASURED_PEAKS.json)",
+        "flop_frac": tile_pairs * POINT_PAIRS_PER_CLOUD_PAIR * FLOP_PER_POINT_PAIR / (kernel_ms * 1e-3) / 1e12 / peak_tflops,
+        "frac_at_observed_clock": achieved_tflops / (2.0 * lanes * obs_mhz * 1e6 / 1e12),
+        "sms": props.multi_processor_count,
+    }
+    line = {
+        "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+        "ms_per_step": ms_total / args.steps, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
+        "dtype": "f32", "data": "synthetic",
+        "config": {"workload": WORKLOAD if nc == N_CLOUDS else "allpairs_cd_%dx%d_clouds_2048pts" % (nc, nc),
+                   "clouds": [nc, nc], "points_per_cloud": N_PTS, "partition": "%dx%d rank grid, all_gather of scalars" % pdist.rank_grid(world),
+                   "l2": "256 MiB memset between steps (inside the timed region, ~0.05 ms)"},
+        "e2e": {"value": e2e_value, "unit": UNIT, "ms_per_step": ms_e2e / args.steps,
+                "h2d_bytes_per_step": 2 * nc * N_PTS * 3 * 4, "d2h_bytes_per_step": nc * nc * 4,
+                "api": "pdgn_b200.evaluation_metrics._pairwise_EMD_CD_ on pinned host tensors (.to(device) + .cpu())"},
+        "gpu_launches": 3 * args.steps,
+        "roofline": roofline, "clocks": clocks,
+    }
+    if not args.no_extras:
+        line["knnquery"] = bench_knn(dev, lanes, sm_max_mhz)
+        line["gathers"] = bench_gathers(dev, float(peaks.get("hbm_gbs") or 6650.0), "measured" if peaks.get("hbm_gbs") else "fallback")
+        if world == 1:
+            n_s, n_r = 4, 50
+            rate, dt = cpu_reference_rate(n_s, n_r)
+            line["cpu_baseline"] = {"value": rate, "unit": UNIT, "cores": os.cpu_count() or 1, "kind": "port", "seconds": dt,
+                                    "sample": "%d x %d cloud pairs of 2048 points (reference Gram-form distChamfer loop, batch_size 50)" % (n_s, n_r)}
+    # sanity: the e2e result equals the device-resident one
+    line["e2e"]["matches_device_result"] = bool(torch.equal(out.cpu(), out_e2e))
+    print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
+def _time_ms(fn, reps, flush):
+    import torch
+    fn()
+    torch.cuda.synchronize()
+    tot = 0.0
+    for _ in range(reps):
+        flush.zero_()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        fn()
+        e1.record()
+        torch.cuda.synchronize()
+        tot += e0.elapsed_time(e1)
+    return tot / reps
+
+
+def bench_knn(dev, lanes, sm_max_mhz):
+    """BASELINE config 2: knnquery k=20 on B=35 x 2048 xyz points (self query)."""
+    import numpy as np
+    import torch
+    from pdgn_b200 import ops
+    rng = np.random.default_rng(0)
+    xyz = torch.from_numpy(rng.uniform(-1, 1, (35, 2048, 3)).astype(np.float32)).to(dev)
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
+    ms = _time_ms(lambda: ops.knn_xyz(20, xyz), 10, flush)
+    q = 35 * 2048
+    inst = q * 2048 * FMA_PIPE_INSTR_PER_POINT_PAIR / (ms * 1e-3)
+    return {"mqueries_per_s": q / (ms * 1e-3) / 1e6, "ms": ms, "shape": "B=35 n=m=2048 k=20",
+            "fp32_issue_frac": inst / (lanes * sm_max_mhz * 1e6)}
+
+
+def bench_gathers(dev, hbm_gbs, src):
+    """Grouping fwd/bwd on the live shape (C=3) and the feature-sized stress shape; algorithmic bytes per SURVEY.md 8d."""
+    import numpy as np
+    import torch
+    from pdgn_b200 import ops
+    rng = np.random.default_rng(0)
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
+    res = {"hbm_peak_gbs": hbm_gbs, "hbm_peak_source": src}
+    for tag, (b, c, n, m, k) in {"c3_live": (35, 3, 2048, 2048, 20), "c256_stress": (35, 256, 1024, 1024, 10)}.items():
+        feat = torch.from_numpy(rng.standard_normal((b, c, n)).astype(np.float32)).to(dev)
+        idx = torch.from_numpy(rng.integers(0, n, (b, m, k)).astype(np.int32)).to(dev)
+        go = torch.from_numpy(rng.standard_normal((b, c, m, k)).astype(np.float32)).to(dev)
+        out = torch.empty((b, c, m, k), dtype=torch.float32, device=dev)
+        grad = torch.zeros((b, c, n), dtype=torch.float32, device=dev)
+        from pdgn_b200._lib import lib
+        L = lib()
+        st = torch.cuda.current_stream().cuda_stream
+        f_ms = _time_ms(lambda: L.pdgn_group_fwd(feat.data_ptr(), idx.data_ptr(), b, c, n, m, k, out.data_ptr(), st), 10, flush)
+        b_ms = _time_ms(lambda: L.pdgn_group_bwd(go.data_ptr(), idx.data_ptr(), b, c, n, m, k, grad.data_ptr(), st), 10, flush)
+        bytes_fwd = 4.0 * (b * c * m * k + b * m * k + b * c * n)
+        res[tag] = {"fwd_ms": f_ms, "fwd_gbs": bytes_fwd / (f_ms * 1e-3) / 1e9, "fwd_frac": bytes_fwd / (f_ms * 1e-3) / 1e9 / hbm_gbs,
+                    "bwd_ms": b_ms, "bwd_gbs": bytes_fwd / (b_ms * 1e-3) / 1e9, "bwd_frac": bytes_fwd / (b_ms * 1e-3) / 1e9 / hbm_gbs,
+                    "algorithmic_mb": bytes_fwd / 1e6}
+    return res
+
+
+if __name__ == "__main__":
+    main()

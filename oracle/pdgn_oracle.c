@@ -1,0 +1,255 @@
+/*
+ * pdgn_oracle.c -- CPU restatement of the reference's nearest-neighbour / distance hot path.
+ *
+ * TEST INFRASTRUCTURE ONLY.  Nothing under pdgn_b200/ may import, link or call this file; it is
+ * used by tests/, __graft_entry__.smoke() and bench.py's cpu_baseline / --impl reference legs as the
+ * checker the CUDA kernels are compared against.
+ *
+ * Parity status: the reference ships no tests or golden vectors for this path, so
+ * the arithmetic here is pinned by (i) the SASS of the reference kernels recompiled with nvcc 12.9 for
+ * sm_100a (see oracle/Makefile target `ref`; the FMUL/FFMA order below was read from cuobjdump) and
+ * (ii) tests/test_ref_kernels.py, which runs those recompiled reference kernels (oracle/_ref) on the
+ * GPU box against this file bit for bit.
+ *
+ * Build: gcc -O2 -ffp-contract=off -fopenmp -shared -fPIC (no contraction by the host compiler: every
+ * fused operation below is an explicit fmaf()).
+ *
+ * All citations are path:line under /root/reference.
+ */
+#include <math.h>
+#include <stdint.h>
+#include <stdlib.h>
+#include <string.h>
+
+/* Squared xyz distance exactly as nvcc 12.9 -O2 compiles
+ *   (qx-px)*(qx-px) + (qy-py)*(qy-py) + (qz-pz)*(qz-pz)
+ * in lib/pointops/src/knnquery/knnquery_cuda_kernel.cu:31,
+ *    lib/pointops/src/interpolation/interpolation_cuda_kernel.cu:153 and
+ *    evaluation/pytorch_structural_losses/src/nndistance.cu:25-28:
+ * FADD dy; FADD dx; FMUL dy*dy; FADD dz; FFMA dx*dx+; FFMA dz*dz+   (the y product is the rounded one). */
+static inline float d2_xyz(float qx, float qy, float qz, float px, float py, float pz) {
+    float dx = qx - px, dy = qy - py, dz = qz - pz;
+    float t = dy * dy;
+    t = fmaf(dx, dx, t);
+    t = fmaf(dz, dz, t);
+    return t;
+}
+
+/* Generic-D squared distance used by the new chamfer / feature-space kernels (no native reference
+ * arithmetic exists for D != 3: the reference uses cuBLAS Gram matrices there, chamfer_loss.py:23-38,
+ * PDGNet_v2.py:449-454).  Contract of the new kernels: D==3 uses the native xyz chain above; otherwise
+ * t = diff_0^2 (rounded), then t = fmaf(diff_c, diff_c, t) for c = 1..D-1 in order. */
+static inline float d2_generic(const float *a, long sa, const float *b, long sb, int D) {
+    if (D == 3) return d2_xyz(a[0], a[sa], a[2 * sa], b[0], b[sb], b[2 * sb]);
+    float diff = a[0] - b[0];
+    float t = diff * diff;
+    for (int c = 1; c < D; ++c) {
+        diff = a[c * sa] - b[c * sb];
+        t = fmaf(diff, diff, t);
+    }
+    return t;
+}
+
+/* knnquery: lib/pointops/src/knnquery/knnquery_cuda_kernel.cu:6-50.
+ * Sequential scan, insertion with strict '<' against double best[] initialised to 1e40, idx to 0.
+ * => ascending (d2, index); NaN / +inf distances never inserted; n < k leaves idx 0 / dist +inf. */
+void oracle_knn_xyz(const float *xyz, const float *new_xyz, int b, int n, int m, int k, int *idx, float *dist2) {
+#pragma omp parallel for collapse(2) schedule(static)
+    for (int bi = 0; bi < b; ++bi) {
+        for (int q = 0; q < m; ++q) {
+            double best[256];
+            int besti[256];
+            const float *P = xyz + (long)bi * n * 3;
+            const float *Q = new_xyz + ((long)bi * m + q) * 3;
+            for (int i = 0; i < k; ++i) { best[i] = 1e40; besti[i] = 0; }
+            for (int c = 0; c < n; ++c) {
+                float d2 = d2_xyz(Q[0], Q[1], Q[2], P[c * 3], P[c * 3 + 1], P[c * 3 + 2]);
+                for (int j = 0; j < k; ++j) {
+                    if ((double)d2 < best[j]) {
+                        for (int i = k - 1; i > j; --i) { best[i] = best[i - 1]; besti[i] = besti[i - 1]; }
+                        best[j] = d2; besti[j] = c;
+                        break;
+                    }
+                }
+            }
+            long o = ((long)bi * m + q) * k;
+            for (int i = 0; i < k; ++i) {
+                idx[o + i] = besti[i];
+                if (dist2) dist2[o + i] = (float)best[i];  /* 1e40 -> +inf, as the device double->float store does */
+            }
+        }
+    }
+}
+
+/* nearestneighbor (3-NN): lib/pointops/src/interpolation/interpolation_cuda_kernel.cu:134-176.
+ * Returns SQUARED distances (the sqrt is taken in pointops.py:77). */
+void oracle_nn3(const float *unknown, const float *known, int b, int n, int m, float *dist2, int *idx) {
+#pragma omp parallel for collapse(2) schedule(static)
+    for (int bi = 0; bi < b; ++bi) {
+        for (int q = 0; q < n; ++q) {
+            const float *U = unknown + ((long)bi * n + q) * 3;
+            const float *K = known + (long)bi * m * 3;
+            double b1 = 1e40, b2 = 1e40, b3 = 1e40;
+            int i1 = 0, i2 = 0, i3 = 0;
+            for (int c = 0; c < m; ++c) {
+                float d = d2_xyz(U[0], U[1], U[2], K[c * 3], K[c * 3 + 1], K[c * 3 + 2]);
+                if (d < b1) { b3 = b2; i3 = i2; b2 = b1; i2 = i1; b1 = d; i1 = c; }
+                else if (d < b2) { b3 = b2; i3 = i2; b2 = d; i2 = c; }
+                else if (d < b3) { b3 = d; i3 = c; }
+            }
+            long o = ((long)bi * n + q) * 3;
+            dist2[o] = (float)b1; dist2[o + 1] = (float)b2; dist2[o + 2] = (float)b3;
+            idx[o] = i1; idx[o + 1] = i2; idx[o + 2] = i3;
+        }
+    }
+}
+
+/* grouping forward: lib/pointops/src/grouping/grouping_cuda_kernel.cu:60-75.
+ * out[b,c,j,s] = points[b,c,idx[b,j,s]] */
+void oracle_group_fwd(const float *points, const int *idx, int b, int c, int n, int m, int k, float *out) {
+#pragma omp parallel for collapse(2) schedule(static)
+    for (int bi = 0; bi < b; ++bi)
+        for (int ci = 0; ci < c; ++ci) {
+            const float *src = points + ((long)bi * c + ci) * n;
+            const int *ix = idx + (long)bi * m * k;
+            float *dst = out + ((long)bi * c + ci) * m * k;
+            for (long e = 0; e < (long)m * k; ++e) dst[e] = src[ix[e]];
+        }
+}
+
+/* grouping backward: grouping_cuda_kernel.cu:28-46 (atomicAdd, order unspecified).
+ * The oracle accumulates in double and adds the rounded total onto grad_points. */
+void oracle_group_bwd(const float *grad_out, const int *idx, int b, int c, int n, int m, int k, float *grad_points) {
+#pragma omp parallel for collapse(2) schedule(static)
+    for (int bi = 0; bi < b; ++bi)
+        for (int ci = 0; ci < c; ++ci) {
+            double *acc = (double *)calloc((size_t)n, sizeof(double));
+            const float *g = grad_out + ((long)bi * c + ci) * m * k;
+            const int *ix = idx + (long)bi * m * k;
+            for (long e = 0; e < (long)m * k; ++e) acc[ix[e]] += (double)g[e];
+            float *dst = grad_points + ((long)bi * c + ci) * n;
+            for (int p = 0; p < n; ++p) dst[p] = (float)((double)dst[p] + acc[p]);
+            free(acc);
+        }
+}
+
+/* interpolation forward: interpolation_cuda_kernel.cu:181-195.  Source order w0*p0 + w1*p1 + w2*p2,
+ * compiled by nvcc 12.9 -O2 to FMUL w1*p1; FFMA w0*p0+; FFMA w2*p2+ (read from SASS). */
+void oracle_interp_fwd(const float *points, const int *idx, const float *weight, int b, int c, int m, int n, float *out) {
+#pragma omp parallel for collapse(2) schedule(static)
+    for (int bi = 0; bi < b; ++bi)
+        for (int ci = 0; ci < c; ++ci) {
+            const float *src = points + ((long)bi * c + ci) * m;
+            for (int j = 0; j < n; ++j) {
+                const int *ix = idx + ((long)bi * n + j) * 3;
+                const float *w = weight + ((long)bi * n + j) * 3;
+                float t = w[1] * src[ix[1]];
+                t = fmaf(w[0], src[ix[0]], t);
+                t = fmaf(w[2], src[ix[2]], t);
+                out[((long)bi * c + ci) * n + j] = t;
+            }
+        }
+}
+
+/* interpolation backward: interpolation_cuda_kernel.cu:90-114: three atomicAdd(g * w_t) per element;
+ * each product is rounded to float first, the sum order is unspecified => double accumulation here. */
+void oracle_interp_bwd(const float *grad_out, const int *idx, const float *weight, int b, int c, int n, int m, float *grad_points) {
+#pragma omp parallel for collapse(2) schedule(static)
+    for (int bi = 0; bi < b; ++bi)
+        for (int ci = 0; ci < c; ++ci) {
+            double *acc = (double *)calloc((size_t)m, sizeof(double));
+            const float *g = grad_out + ((long)bi * c + ci) * n;
+            for (int j = 0; j < n; ++j) {
+                const int *ix = idx + ((long)bi * n + j) * 3;
+                const float *w = weight + ((long)bi * n + j) * 3;
+                for (int t = 0; t < 3; ++t) { float pr = g[j] * w[t]; acc[ix[t]] += (double)pr; }
+            }
+            float *dst = grad_points + ((long)bi * c + ci) * m;
+            for (int p = 0; p < m; ++p) dst[p] = (float)((double)dst[p] + acc[p]);
+            free(acc);
+        }
+}
+
+/* Directional nearest-neighbour distance with argmin, generic D.
+ * D == 3 follows evaluation/pytorch_structural_losses/src/nndistance.cu:2-124 (NmDistanceKernel):
+ * first element taken unconditionally, then strict '<' => lowest index among equal minima; across the
+ * kernel's 512-point tiles `result > best` is strict too, so the earliest tile wins. */
+void oracle_nn_min(const float *x, const float *y, int b, int nx, int ny, int D, float *mind, int *argm) {
+#pragma omp parallel for collapse(2) schedule(static)
+    for (int bi = 0; bi < b; ++bi)
+        for (int i = 0; i < nx; ++i) {
+            const float *X = x + ((long)bi * nx + i) * D;
+            const float *Y = y + (long)bi * ny * D;
+            float best = 0.f; int besti = 0;
+            for (int j = 0; j < ny; ++j) {
+                float d = d2_generic(X, 1, Y + (long)j * D, 1, D);
+                if (j == 0 || d < best) { best = d; besti = j; }
+            }
+            mind[(long)bi * nx + i] = best;
+            if (argm) argm[(long)bi * nx + i] = besti;
+        }
+}
+
+/* NNDistance both directions (structural_loss.cpp:80-99 / nndistance.cu:125-128). */
+void oracle_nndistance(const float *xyz1, const float *xyz2, int b, int n, int m,
+                       float *dist1, int *idx1, float *dist2, int *idx2) {
+    oracle_nn_min(xyz1, xyz2, b, n, m, 3, dist1, idx1);
+    oracle_nn_min(xyz2, xyz1, b, m, n, 3, dist2, idx2);
+}
+
+/* All-pairs Chamfer matrix: evaluation/evaluation_metrics.py:85-121 (_pairwise_EMD_CD_) with the
+ * native direct-difference distance (nndistance.cu) instead of the Gram form of distChamfer (:35-45):
+ * out[s,r] = mean_i min_j d(A_s[i],B_r[j]) + mean_j min_i d(A_s[i],B_r[j]).
+ * Min values are exact FP32; the two means are taken in double and rounded once. */
+void oracle_cd_allpairs(const float *A, const float *B, int na, int nb, int npts, float *out) {
+#pragma omp parallel for collapse(2) schedule(dynamic, 1)
+    for (int s = 0; s < na; ++s)
+        for (int r = 0; r < nb; ++r) {
+            const float *X = A + (long)s * npts * 3, *Y = B + (long)r * npts * 3;
+            float *colmin = (float *)malloc(sizeof(float) * (size_t)npts);
+            double rs = 0.0, cs = 0.0;
+            for (int j = 0; j < npts; ++j) colmin[j] = INFINITY;
+            for (int i = 0; i < npts; ++i) {
+                float rm = INFINITY;
+                for (int j = 0; j < npts; ++j) {
+                    float d = d2_xyz(X[i * 3], X[i * 3 + 1], X[i * 3 + 2], Y[j * 3], Y[j * 3 + 1], Y[j * 3 + 2]);
+                    rm = d < rm ? d : rm;
+                    colmin[j] = d < colmin[j] ? d : colmin[j];
+                }
+                rs += rm;
+            }
+            for (int j = 0; j < npts; ++j) cs += colmin[j];
+            out[(long)s * nb + r] = (float)(rs / npts + cs / npts);
+            free(colmin);
+        }
+}
+
+/* Feature-space kNN of the generator: models/PDGNet_v2.py:439-459 / :479-502.  The reference ranks a
+ * cuBLAS Gram matrix with an unstable torch.sort and keeps ranks 1..k; its exact indices are not a
+ * stable target (SURVEY.md section 7 "Gram-form parity").  Contract of the new kernel, restated here:
+ * exact FP32 direct distances (d2_generic over channels, x laid out [B,C,N]), total order (d2, index),
+ * ranks skip..skip+k-1 (skip=1 reproduces "drop rank 0").  idx is int64 like torch.sort's. */
+typedef struct { float d; int i; } oracle_pair_t;
+static int cmp_pair(const void *a, const void *b) {
+    const oracle_pair_t *p = (const oracle_pair_t *)a, *q = (const oracle_pair_t *)b;
+    if (p->d < q->d) return -1;
+    if (p->d > q->d) return 1;
+    return (p->i > q->i) - (p->i < q->i);
+}
+void oracle_knn_feat(const float *x, int b, int c, int n, int k, int skip, int64_t *idx, float *dist2) {
+#pragma omp parallel for collapse(2) schedule(static)
+    for (int bi = 0; bi < b; ++bi)
+        for (int i = 0; i < n; ++i) {
+            const float *X = x + (long)bi * c * n;
+            oracle_pair_t *pr = (oracle_pair_t *)malloc(sizeof(oracle_pair_t) * (size_t)n);
+            for (int j = 0; j < n; ++j) { pr[j].d = d2_generic(X + i, n, X + j, n, c); pr[j].i = j; }
+            qsort(pr, (size_t)n, sizeof(oracle_pair_t), cmp_pair);
+            for (int t = 0; t < k; ++t) {
+                idx[((long)bi * n + i) * k + t] = pr[skip + t].i;
+                if (dist2) dist2[((long)bi * n + i) * k + t] = pr[skip + t].d;
+            }
+            free(pr);
+        }
+}
+
+int oracle_abi_version(void) { return 1; }

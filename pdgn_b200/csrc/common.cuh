@@ -1,0 +1,88 @@
+// common.cuh -- shared device helpers for libpdgn_b200 (sm_100a only).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include "../../include/pdgn_b200.h"
+
+#if defined(__CUDA_ARCH__) && (__CUDA_ARCH__ < 1000)
+#error "libpdgn_b200 is written for sm_100a (B200) only"
+#endif
+
+namespace pdgn {
+
+constexpr int kWarp = 32;
+constexpr unsigned kFull = 0xffffffffu;
+
+// Squared xyz distance with the operation order the reference kernels compile to under nvcc 12.9 -O2
+// (knnquery_cuda_kernel.cu:31, interpolation_cuda_kernel.cu:153, nndistance.cu:25-28; order read from SASS):
+// FMUL on the y difference, then FFMA x, then FFMA z.  Explicit intrinsics: no reliance on contraction.
+__device__ __forceinline__ float d2_xyz(float qx, float qy, float qz, float px, float py, float pz) {
+    const float dx = __fsub_rn(qx, px), dy = __fsub_rn(qy, py), dz = __fsub_rn(qz, pz);
+    return __fmaf_rn(dz, dz, __fmaf_rn(dx, dx, __fmul_rn(dy, dy)));
+}
+
+// 3-input min: one FMNMX3 on sm_100a.
+__device__ __forceinline__ float min3(float a, float b, float c) { return fminf(fminf(a, b), c); }
+
+__device__ __forceinline__ float warp_sum(float v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(kFull, v, o);
+    return v;
+}
+
+constexpr float kInf = __builtin_huge_valf();
+
+// insert (d, j) into the ascending list (column `col` of ld/li, stride `stride`), keeping k entries.
+// Precondition: d < ld[(k-1)*stride + col].  Equal distances keep their arrival (= index) order.
+__device__ __forceinline__ void list_insert(float* ld, int* li, int stride, int col, int k, float d, int j) {
+    int pos = k - 1;
+    while (pos > 0) {
+        const float prev = ld[(pos - 1) * stride + col];
+        if (!(prev > d)) break;
+        ld[pos * stride + col] = prev;
+        li[pos * stride + col] = li[(pos - 1) * stride + col];
+        --pos;
+    }
+    ld[pos * stride + col] = d;
+    li[pos * stride + col] = j;
+}
+
+// ---- mbarrier + 1-D bulk async copy (TMA engine, SASS UBLKCP) ------------------------------------------
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint64_t* bar, unsigned count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_fence_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, unsigned bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, unsigned parity) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "WAIT_%=:\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
+        "@p bra DONE_%=;\n\t"
+        "bra WAIT_%=;\n\t"
+        "DONE_%=:\n\t}" ::"r"(smem_u32(bar)), "r"(parity) : "memory");
+}
+// global -> shared bulk copy; bytes % 16 == 0, both addresses 16-byte aligned; completes on `bar`.
+__device__ __forceinline__ void bulk_g2s(void* dst_smem, const void* src_gmem, unsigned bytes, uint64_t* bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+                     smem_u32(dst_smem)), "l"(src_gmem), "r"(bytes), "r"(smem_u32(bar)) : "memory");
+}
+// order prior generic-proxy smem accesses before later async-proxy (bulk copy) writes to the same buffer
+__device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+
+}  // namespace pdgn
+
+#define PDGN_CHECK_LAUNCH()                          \
+    do {                                             \
+        cudaError_t e__ = cudaGetLastError();        \
+        if (e__ != cudaSuccess) return (int)e__;     \
+    } while (0)
+#define PDGN_CUDA(call)                              \
+    do {                                             \
+        cudaError_t e__ = (call);                    \
+        if (e__ != cudaSuccess) return (int)e__;     \
+    } while (0)
