@@ -336,12 +336,15 @@ def test_against_recompiled_reference_knn_and_nn3(dev):
     rng = np.random.default_rng(21)
     for maker, b, n, m, k in [(clouds_uniform, 4, 2048, 2048, 20), (clouds_sphere, 3, 1024, 256, 20), (clouds_ties, 2, 512, 512, 20)]:
         xyz, q = maker(rng, b, n, 3), maker(rng, b, m, 3)
-        ridx, rd2 = rk.knnquery(k, G(xyz, dev), G(q, dev))
+        # NB the reference kernel never offsets its dist2 pointer per query (knnquery_cuda_kernel.cu:11-13 offsets
+        # new_xyz, xyz and idx only), so every thread races on dist2[0:k]; pointops.py:426-428 discards it.  Only
+        # idx is comparable; our dist2 is checked against the oracle in test_knn_xyz_bit_exact.
+        ridx, _ = rk.knnquery(k, G(xyz, dev), G(q, dev))
         idx, d2 = ops.knn_xyz(k, G(xyz, dev), G(q, dev), return_dist=True)
-        assert torch.equal(idx, ridx) and torch.equal(d2, rd2)
+        assert torch.equal(idx, ridx)
         oidx, od2 = ocpu.knn_xyz(xyz, q, k)
         np.testing.assert_array_equal(C(ridx), oidx)  # the oracle itself is pinned by the reference kernel
-        np.testing.assert_array_equal(C(rd2), od2)
+        np.testing.assert_array_equal(C(d2), od2)
     unk, kn = clouds_sphere(rng, 3, 2048, 3), clouds_sphere(rng, 3, 1024, 3)
     rd2, ridx = rk.nn3(G(unk, dev), G(kn, dev))
     d2, idx = ops.nn3(G(unk, dev), G(kn, dev))
