@@ -16,162 +16,17 @@
 //     (FMNMX3), reduced across the warp with one CREDUX.MIN on the bit pattern (distances are >= 0 so uint
 //     order == float order) and merged across the half's 4 warps with one shared-memory ATOMS.MIN.
 //   * Per cloud pair only one scalar leaves the SM: (sum_i rowmin + sum_j colmin) / npts.
-#include "common.cuh"
+#include "cd_kernel.cuh"
 
 namespace pdgn {
 
-constexpr int CD_R = 16;                    // rows (points of the A cloud) per thread
-constexpr int CD_HALF = 128;                // threads per half
-constexpr int CD_THREADS = 2 * CD_HALF;
-constexpr int CD_ROWS = CD_R * CD_HALF;     // 2048 rows per half per row block
-constexpr int CD_TILE = 2048;               // candidates per shared-memory stage
-constexpr unsigned CD_INF_BITS = 0x7f800000u;
-
-// AoS [cloud][npts][3] -> SoA planes [cloud][3][npad]; pad entries replicate point 0 (harmless for minima).
-__global__ void cd_pack_kernel(const float* __restrict__ src, int cloud0, int npts, int npad, float* __restrict__ dst) {
-    const int cl = blockIdx.y;
-    const int j = blockIdx.x * blockDim.x + threadIdx.x;
-    if (j >= npad) return;
-    const float* p = src + ((size_t)(cloud0 + cl) * npts + (j < npts ? j : 0)) * 3;
-    float* d = dst + (size_t)cl * 3 * npad + j;
-    d[0] = p[0];
-    d[npad] = p[1];
-    d[2 * (size_t)npad] = p[2];
-}
-
-// Two candidates against the thread's 16 rows.
-__device__ __forceinline__ void cd_two_candidates(const float (&qx)[CD_R], const float (&qy)[CD_R], const float (&qz)[CD_R],
-                                                  float (&rowmin)[CD_R], float x0, float y0, float z0, float x1, float y1,
-                                                  float z1, unsigned* col, int lane) {
-    float c0, c1;
-    {
-        const float a0 = d2_xyz(qx[0], qy[0], qz[0], x0, y0, z0), a1 = d2_xyz(qx[0], qy[0], qz[0], x1, y1, z1);
-        const float b0 = d2_xyz(qx[1], qy[1], qz[1], x0, y0, z0), b1 = d2_xyz(qx[1], qy[1], qz[1], x1, y1, z1);
-        rowmin[0] = min3(rowmin[0], a0, a1);
-        rowmin[1] = min3(rowmin[1], b0, b1);
-        c0 = fminf(a0, b0);
-        c1 = fminf(a1, b1);
-    }
-#pragma unroll
-    for (int k = 2; k < CD_R; k += 2) {
-        const float a0 = d2_xyz(qx[k], qy[k], qz[k], x0, y0, z0), a1 = d2_xyz(qx[k], qy[k], qz[k], x1, y1, z1);
-        const float b0 = d2_xyz(qx[k + 1], qy[k + 1], qz[k + 1], x0, y0, z0);
-        const float b1 = d2_xyz(qx[k + 1], qy[k + 1], qz[k + 1], x1, y1, z1);
-        rowmin[k] = min3(rowmin[k], a0, a1);
-        rowmin[k + 1] = min3(rowmin[k + 1], b0, b1);
-        c0 = min3(c0, a0, b0);
-        c1 = min3(c1, a1, b1);
-    }
-    const unsigned r0 = __reduce_min_sync(kFull, __float_as_uint(c0));
-    const unsigned r1 = __reduce_min_sync(kFull, __float_as_uint(c1));
-    if (lane < 2) atomicMin(col + lane, lane ? r1 : r0);
-}
-
-__global__ void __launch_bounds__(CD_THREADS, 2)
-cd_allpairs_kernel(const float* __restrict__ PA, const float* __restrict__ PB, int nrows, int ncols, int npts, int npad,
-                   int rstrip, float* __restrict__ out, long long ld_out) {
-    extern __shared__ __align__(128) unsigned char smem_raw[];
-    float* tile = reinterpret_cast<float*>(smem_raw);                 // [2 stages][3 planes][CD_TILE]
-    unsigned* colmin = reinterpret_cast<unsigned*>(tile + 2 * 3 * CD_TILE);  // [2 halves][npad]
-    float* red = reinterpret_cast<float*>(colmin + 2 * (size_t)npad);        // [2 halves][4 warps]
-    uint64_t* bars = reinterpret_cast<uint64_t*>(red + 8);                  // [2 stages]
-
-    const int tid = threadIdx.x, half = tid >> 7, ht = tid & (CD_HALF - 1), lane = tid & 31, hw = ht >> 5;
-    int s = blockIdx.y * 2 + half;
-    const bool s_valid = s < nrows;
-    if (!s_valid) s = nrows - 1;  // odd row count: the spare half recomputes the last cloud and discards it
-    const int r_begin = blockIdx.x * rstrip;
-    const int r_end = min(ncols, r_begin + rstrip);
-    const int nrb = (npts + CD_ROWS - 1) / CD_ROWS;
-    const int ncb = (npad + CD_TILE - 1) / CD_TILE;
-    const int ntiles = (r_end - r_begin) * nrb * ncb;
-    unsigned* mycol = colmin + (size_t)half * npad;
-
-    for (int j = ht; j < npad; j += CD_HALF) mycol[j] = CD_INF_BITS;
-    if (tid == 0) {
-        mbar_init(&bars[0], 1);
-        mbar_init(&bars[1], 1);
-        mbar_fence_init();
-    }
-    __syncthreads();
-
-    // tile t (flattened over r, row block, candidate block) -> stage t&1
-    auto issue = [&](int t) {
-        const int cb = t % ncb;
-        const int r = r_begin + t / (ncb * nrb);
-        const int c0 = cb * CD_TILE;
-        const unsigned bytes = (unsigned)min(CD_TILE, npad - c0) * 4u;
-        uint64_t* bar = &bars[t & 1];
-        float* dst = tile + (t & 1) * 3 * CD_TILE;
-        const float* src = PB + (size_t)r * 3 * npad + c0;
-        mbar_expect_tx(bar, 3u * bytes);
-        bulk_g2s(dst, src, bytes, bar);
-        bulk_g2s(dst + CD_TILE, src + npad, bytes, bar);
-        bulk_g2s(dst + 2 * CD_TILE, src + 2 * (size_t)npad, bytes, bar);
-    };
-    if (tid == 0) {
-        issue(0);
-        if (ntiles > 1) issue(1);
-    }
-
-    float qx[CD_R], qy[CD_R], qz[CD_R], rowmin[CD_R];
-    const float* arow = PA + (size_t)s * 3 * npad;
-    const float inv_n = 1.0f / (float)npts;
-    int t = 0;
-    for (int r = r_begin; r < r_end; ++r) {
-        float total = 0.f;
-        for (int rb = 0; rb < nrb; ++rb) {
-            const int i0 = rb * CD_ROWS + ht * CD_R;
-            if (nrb > 1 || r == r_begin) {
-#pragma unroll
-                for (int k = 0; k < CD_R; ++k) {
-                    const int i = (i0 + k < npts) ? i0 + k : 0;
-                    qx[k] = arow[i];
-                    qy[k] = arow[npad + i];
-                    qz[k] = arow[2 * (size_t)npad + i];
-                }
-            }
-#pragma unroll
-            for (int k = 0; k < CD_R; ++k) rowmin[k] = __int_as_float(CD_INF_BITS);
-
-            for (int cb = 0; cb < ncb; ++cb, ++t) {
-                const float* st = tile + (t & 1) * 3 * CD_TILE;
-                const int cnt = min(CD_TILE, npad - cb * CD_TILE);
-                unsigned* col = mycol + cb * CD_TILE;
-                mbar_wait(&bars[t & 1], (unsigned)((t >> 1) & 1));
-#pragma unroll 1
-                for (int j = 0; j < cnt; j += 4) {
-                    const float4 X = *reinterpret_cast<const float4*>(st + j);
-                    const float4 Y = *reinterpret_cast<const float4*>(st + CD_TILE + j);
-                    const float4 Z = *reinterpret_cast<const float4*>(st + 2 * CD_TILE + j);
-                    cd_two_candidates(qx, qy, qz, rowmin, X.x, Y.x, Z.x, X.y, Y.y, Z.y, col + j, lane);
-                    cd_two_candidates(qx, qy, qz, rowmin, X.z, Y.z, Z.z, X.w, Y.w, Z.w, col + j + 2, lane);
-                }
-                __syncthreads();  // stage drained by all 8 warps; this tile's column atomics are done
-                if (tid == 0 && t + 2 < ntiles) {
-                    fence_proxy_async();
-                    issue(t + 2);
-                }
-            }
-            const int nvalid = npts - i0;
-#pragma unroll
-            for (int k = 0; k < CD_R; ++k)
-                if (k < nvalid) total += rowmin[k];
-        }
-        // cloud pair (s, r) complete: fold this half's column minima, reset them for the next r
-        for (int j = ht; j < npad; j += CD_HALF) {
-            if (j < npts) total += __uint_as_float(mycol[j]);
-            mycol[j] = CD_INF_BITS;
-        }
-        total = warp_sum(total);
-        if (lane == 0) red[half * 4 + hw] = total;
-        __syncthreads();
-        if (ht == 0 && s_valid) {
-            const float* rr = red + half * 4;
-            out[(size_t)s * ld_out + r] = (rr[0] + rr[1] + rr[2] + rr[3]) * inv_n;
-        }
-    }
-}
+// shipped configuration (chosen with tools/cd_tune.cu on B200; see DESIGN.md / profiles/)
+constexpr int CD_R = 16;      // rows per thread
+constexpr int CD_NH = 2;      // halves (A clouds) per CTA
+constexpr int CD_MINB = 2;    // CTAs per SM the register allocation must allow
+constexpr int CD_VARIANT = CDV_PRED_RED | CDV_PREFETCH;  // +2.3 % over the plain loop (profiles/r01_cd_tune_*.txt)
+constexpr int CD_THREADS = CD_NH * CD_HALF;
+#define PDGN_CD_KERNEL cd_allpairs_kernel<CD_R, CD_NH, CD_MINB, CD_VARIANT>
 
 static int cd_num_sms() {
     static int sms = 0;
@@ -217,18 +72,18 @@ extern "C" int pdgn_cd_allpairs(const float* A, const float* B, int na, int nb, 
     cd_pack_kernel<<<pgb, pb, 0, st>>>(B, col0, npts, npad, PB);
     PDGN_CHECK_LAUNCH();
 
-    const size_t smem = (size_t)(2 * 3 * CD_TILE + 2 * (size_t)npad + 8) * 4 + 2 * sizeof(uint64_t);
-    PDGN_CUDA(cudaFuncSetAttribute(cd_allpairs_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    const int spairs = (nrows + 1) / 2;
+    const size_t smem = cd_smem_bytes<CD_NH, CD_VARIANT>(npad);
+    PDGN_CUDA(cudaFuncSetAttribute(PDGN_CD_KERNEL, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    const int spairs = (nrows + CD_NH - 1) / CD_NH;
     if (spairs > 65535) return PDGN_ERR_UNSUPPORTED;
     // enough CTAs for >= ~20 waves of 2 CTAs/SM so the tail is small; each CTA walks `rstrip` B clouds
-    const int target = 20 * 2 * cd_num_sms();
+    const int target = 20 * CD_MINB * cd_num_sms();
     int strips = (target + spairs - 1) / spairs;
     if (strips > ncols) strips = ncols;
     if (strips < 1) strips = 1;
     const int rstrip = (ncols + strips - 1) / strips;
     strips = (ncols + rstrip - 1) / rstrip;
-    cd_allpairs_kernel<<<dim3(strips, spairs), CD_THREADS, smem, st>>>(PA, PB, nrows, ncols, npts, npad, rstrip, out, ld_out);
+    PDGN_CD_KERNEL<<<dim3(strips, spairs), CD_THREADS, smem, st>>>(PA, PB, nrows, ncols, npts, npad, rstrip, out, ld_out);
     PDGN_CHECK_LAUNCH();
     return PDGN_OK;
 }

@@ -1,0 +1,257 @@
+// cd_kernel.cuh -- device code of the all-pairs Chamfer kernel (see cd_allpairs.cu for the design notes).
+// Templated so that tools/cd_tune.cu can instantiate variants; the library instantiates CdConfig (cd_allpairs.cu).
+#pragma once
+#include "common.cuh"
+
+namespace pdgn {
+
+constexpr int CD_HALF = 128;                // threads per half (one A cloud per half)
+constexpr int CD_TILE = 2048;               // candidates per shared-memory stage
+constexpr unsigned CD_INF_BITS = 0x7f800000u;
+
+// variant bits (tuning switches; the shipped combination is CD_VARIANT in cd_allpairs.cu)
+constexpr int CDV_PRED_RED = 1;    // predicated red.shared.min (inline PTX) instead of a divergent branch around atomicMin
+constexpr int CDV_PREFETCH = 2;    // software-pipelined LDS.128 of the next 4 candidates
+constexpr int CDV_RED4 = 4;        // one shared atomic per 4 candidates (lanes 0..3) instead of one per 2
+constexpr int CDV_AOS = 8;         // candidates staged as float4 (x,y,z,0): x/z always land in even registers, y in odd
+
+// AoS [cloud][npts][3] -> SoA planes [cloud][3][npad]; pad entries replicate point 0 (harmless for minima).
+__global__ void cd_pack_kernel(const float* __restrict__ src, int cloud0, int npts, int npad, float* __restrict__ dst) {
+    const int cl = blockIdx.y;
+    const int j = blockIdx.x * blockDim.x + threadIdx.x;
+    if (j >= npad) return;
+    const float* p = src + ((size_t)(cloud0 + cl) * npts + (j < npts ? j : 0)) * 3;
+    float* d = dst + (size_t)cl * 3 * npad + j;
+    d[0] = p[0];
+    d[npad] = p[1];
+    d[2 * (size_t)npad] = p[2];
+}
+
+// AoS [cloud][npts][3] -> padded AoS [cloud][npad] float4 (x,y,z,0) for the CDV_AOS candidate layout.
+__global__ void cd_pack4_kernel(const float* __restrict__ src, int cloud0, int npts, int npad, float4* __restrict__ dst) {
+    const int cl = blockIdx.y;
+    const int j = blockIdx.x * blockDim.x + threadIdx.x;
+    if (j >= npad) return;
+    const float* p = src + ((size_t)(cloud0 + cl) * npts + (j < npts ? j : 0)) * 3;
+    dst[(size_t)cl * npad + j] = make_float4(p[0], p[1], p[2], 0.f);
+}
+
+__device__ __forceinline__ void red_min_shared_pred(unsigned* addr, unsigned v, bool pred) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "setp.ne.u32 p, %2, 0;\n\t"
+        "@p red.shared.min.u32 [%0], %1;\n\t}" ::"r"(smem_u32(addr)), "r"(v), "r"((unsigned)pred) : "memory");
+}
+
+// Two candidates against the thread's R rows: updates the row minima, returns the two column partial minima.
+template <int R>
+__device__ __forceinline__ void cd_two_candidates(const float (&qx)[R], const float (&qy)[R], const float (&qz)[R], float (&rowmin)[R],
+                                                  float x0, float y0, float z0, float x1, float y1, float z1, float& c0, float& c1) {
+    {
+        const float a0 = d2_xyz(qx[0], qy[0], qz[0], x0, y0, z0), a1 = d2_xyz(qx[0], qy[0], qz[0], x1, y1, z1);
+        const float b0 = d2_xyz(qx[1], qy[1], qz[1], x0, y0, z0), b1 = d2_xyz(qx[1], qy[1], qz[1], x1, y1, z1);
+        rowmin[0] = min3(rowmin[0], a0, a1);
+        rowmin[1] = min3(rowmin[1], b0, b1);
+        c0 = fminf(a0, b0);
+        c1 = fminf(a1, b1);
+    }
+#pragma unroll
+    for (int k = 2; k < R; k += 2) {
+        const float a0 = d2_xyz(qx[k], qy[k], qz[k], x0, y0, z0), a1 = d2_xyz(qx[k], qy[k], qz[k], x1, y1, z1);
+        const float b0 = d2_xyz(qx[k + 1], qy[k + 1], qz[k + 1], x0, y0, z0);
+        const float b1 = d2_xyz(qx[k + 1], qy[k + 1], qz[k + 1], x1, y1, z1);
+        rowmin[k] = min3(rowmin[k], a0, a1);
+        rowmin[k + 1] = min3(rowmin[k + 1], b0, b1);
+        c0 = min3(c0, a0, b0);
+        c1 = min3(c1, a1, b1);
+    }
+}
+
+// Four candidates (one LDS.128 per plane): row minima in registers, column minima -> warp CREDUX -> shared atomics.
+template <int R, int VAR>
+__device__ __forceinline__ void cd_four_candidates(const float (&qx)[R], const float (&qy)[R], const float (&qz)[R], float (&rowmin)[R],
+                                                   const float4& X, const float4& Y, const float4& Z, unsigned* col, int lane) {
+    float c0, c1, c2, c3;
+    cd_two_candidates<R>(qx, qy, qz, rowmin, X.x, Y.x, Z.x, X.y, Y.y, Z.y, c0, c1);
+    const unsigned r0 = __reduce_min_sync(kFull, __float_as_uint(c0));
+    const unsigned r1 = __reduce_min_sync(kFull, __float_as_uint(c1));
+    if (!(VAR & CDV_RED4)) {
+        if (VAR & CDV_PRED_RED) red_min_shared_pred(col + lane, lane ? r1 : r0, lane < 2);
+        else if (lane < 2) atomicMin(col + lane, lane ? r1 : r0);
+    }
+    cd_two_candidates<R>(qx, qy, qz, rowmin, X.z, Y.z, Z.z, X.w, Y.w, Z.w, c2, c3);
+    const unsigned r2 = __reduce_min_sync(kFull, __float_as_uint(c2));
+    const unsigned r3 = __reduce_min_sync(kFull, __float_as_uint(c3));
+    if (VAR & CDV_RED4) {
+        const unsigned v = lane == 0 ? r0 : lane == 1 ? r1 : lane == 2 ? r2 : r3;
+        if (VAR & CDV_PRED_RED) red_min_shared_pred(col + lane, v, lane < 4);
+        else if (lane < 4) atomicMin(col + lane, v);
+    } else {
+        if (VAR & CDV_PRED_RED) red_min_shared_pred(col + 2 + lane, lane ? r3 : r2, lane < 2);
+        else if (lane < 2) atomicMin(col + 2 + lane, lane ? r3 : r2);
+    }
+}
+
+// Two candidates given as float4 (x,y,z,-): CDV_AOS path.
+template <int R, int VAR>
+__device__ __forceinline__ void cd_two_candidates_aos(const float (&qx)[R], const float (&qy)[R], const float (&qz)[R], float (&rowmin)[R],
+                                                      const float4& P0, const float4& P1, unsigned* col, int lane) {
+    float c0, c1;
+    cd_two_candidates<R>(qx, qy, qz, rowmin, P0.x, P0.y, P0.z, P1.x, P1.y, P1.z, c0, c1);
+    const unsigned r0 = __reduce_min_sync(kFull, __float_as_uint(c0));
+    const unsigned r1 = __reduce_min_sync(kFull, __float_as_uint(c1));
+    if (VAR & CDV_PRED_RED) red_min_shared_pred(col + lane, lane ? r1 : r0, lane < 2);
+    else if (lane < 2) atomicMin(col + lane, lane ? r1 : r0);
+}
+
+// NH halves of 128 threads per CTA; each half owns one A cloud (R rows per thread, CD_ROWS = R*128 per row block).
+template <int R, int NH, int MINB, int VAR>
+__global__ void __launch_bounds__(NH * CD_HALF, MINB)
+cd_allpairs_kernel(const float* __restrict__ PA, const float* __restrict__ PB, int nrows, int ncols, int npts, int npad,
+                   int rstrip, float* __restrict__ out, long long ld_out) {
+    constexpr int ROWS = R * CD_HALF;
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    constexpr int STAGE = ((VAR & CDV_AOS) ? 4 : 3) * CD_TILE;                // floats per stage
+    float* tile = reinterpret_cast<float*>(smem_raw);                         // [2 stages][3 planes][CD_TILE] or [2][CD_TILE] float4
+    unsigned* colmin = reinterpret_cast<unsigned*>(tile + 2 * STAGE);         // [NH][npad]
+    float* red = reinterpret_cast<float*>(colmin + NH * (size_t)npad);        // [NH][4 warps]
+    uint64_t* bars = reinterpret_cast<uint64_t*>(red + NH * 4);              // [2 stages]
+
+    const int tid = threadIdx.x, half = tid >> 7, ht = tid & (CD_HALF - 1), lane = tid & 31, hw = ht >> 5;
+    int s = blockIdx.y * NH + half;
+    const bool s_valid = s < nrows;
+    if (!s_valid) s = nrows - 1;  // ragged row count: spare halves recompute the last cloud and discard it
+    const int r_begin = blockIdx.x * rstrip;
+    const int r_end = min(ncols, r_begin + rstrip);
+    const int nrb = (npts + ROWS - 1) / ROWS;
+    const int ncb = (npad + CD_TILE - 1) / CD_TILE;
+    const int ntiles = (r_end - r_begin) * nrb * ncb;
+    unsigned* mycol = colmin + (size_t)half * npad;
+
+    for (int j = ht; j < npad; j += CD_HALF) mycol[j] = CD_INF_BITS;
+    if (tid == 0) {
+        mbar_init(&bars[0], 1);
+        mbar_init(&bars[1], 1);
+        mbar_fence_init();
+    }
+    __syncthreads();
+
+    // tile t (flattened over r, row block, candidate block) -> stage t&1
+    auto issue = [&](int t) {
+        const int cb = t % ncb;
+        const int r = r_begin + t / (ncb * nrb);
+        const int c0 = cb * CD_TILE;
+        const unsigned bytes = (unsigned)min(CD_TILE, npad - c0) * 4u;
+        uint64_t* bar = &bars[t & 1];
+        float* dst = tile + (t & 1) * STAGE;
+        if (VAR & CDV_AOS) {
+            mbar_expect_tx(bar, 4u * bytes);
+            bulk_g2s(dst, PB + ((size_t)r * npad + c0) * 4, 4u * bytes, bar);
+        } else {
+            const float* src = PB + (size_t)r * 3 * npad + c0;
+            mbar_expect_tx(bar, 3u * bytes);
+            bulk_g2s(dst, src, bytes, bar);
+            bulk_g2s(dst + CD_TILE, src + npad, bytes, bar);
+            bulk_g2s(dst + 2 * CD_TILE, src + 2 * (size_t)npad, bytes, bar);
+        }
+    };
+    if (tid == 0) {
+        issue(0);
+        if (ntiles > 1) issue(1);
+    }
+
+    float qx[R], qy[R], qz[R], rowmin[R];
+    const float* arow = PA + (size_t)s * 3 * npad;
+    const float inv_n = 1.0f / (float)npts;
+    int t = 0;
+    for (int r = r_begin; r < r_end; ++r) {
+        float total = 0.f;
+        for (int rb = 0; rb < nrb; ++rb) {
+            const int i0 = rb * ROWS + ht * R;
+            if (nrb > 1 || r == r_begin) {
+#pragma unroll
+                for (int k = 0; k < R; ++k) {
+                    const int i = (i0 + k < npts) ? i0 + k : 0;
+                    qx[k] = arow[i];
+                    qy[k] = arow[npad + i];
+                    qz[k] = arow[2 * (size_t)npad + i];
+                }
+            }
+#pragma unroll
+            for (int k = 0; k < R; ++k) rowmin[k] = __int_as_float(CD_INF_BITS);
+
+            for (int cb = 0; cb < ncb; ++cb, ++t) {
+                const float* st = tile + (t & 1) * STAGE;
+                const int cnt = min(CD_TILE, npad - cb * CD_TILE);
+                unsigned* col = mycol + cb * CD_TILE;
+                mbar_wait(&bars[t & 1], (unsigned)((t >> 1) & 1));
+                if (VAR & CDV_AOS) {
+                    const float4* st4 = reinterpret_cast<const float4*>(st);
+                    if (VAR & CDV_PREFETCH) {
+                        float4 P0 = st4[0], P1 = st4[1];
+#pragma unroll 1
+                        for (int j = 0; j < cnt; j += 2) {
+                            const int jn = (j + 2 < cnt) ? j + 2 : j;
+                            const float4 N0 = st4[jn], N1 = st4[jn + 1];
+                            cd_two_candidates_aos<R, VAR>(qx, qy, qz, rowmin, P0, P1, col + j, lane);
+                            P0 = N0; P1 = N1;
+                        }
+                    } else {
+#pragma unroll 2
+                        for (int j = 0; j < cnt; j += 2)
+                            cd_two_candidates_aos<R, VAR>(qx, qy, qz, rowmin, st4[j], st4[j + 1], col + j, lane);
+                    }
+                } else if (VAR & CDV_PREFETCH) {
+                    float4 X = *reinterpret_cast<const float4*>(st);
+                    float4 Y = *reinterpret_cast<const float4*>(st + CD_TILE);
+                    float4 Z = *reinterpret_cast<const float4*>(st + 2 * CD_TILE);
+#pragma unroll 1
+                    for (int j = 0; j < cnt; j += 4) {
+                        const int jn = (j + 4 < cnt) ? j + 4 : j;  // last iteration re-reads its own quad
+                        const float4 Xn = *reinterpret_cast<const float4*>(st + jn);
+                        const float4 Yn = *reinterpret_cast<const float4*>(st + CD_TILE + jn);
+                        const float4 Zn = *reinterpret_cast<const float4*>(st + 2 * CD_TILE + jn);
+                        cd_four_candidates<R, VAR>(qx, qy, qz, rowmin, X, Y, Z, col + j, lane);
+                        X = Xn; Y = Yn; Z = Zn;
+                    }
+                } else {
+#pragma unroll 1
+                    for (int j = 0; j < cnt; j += 4) {
+                        const float4 X = *reinterpret_cast<const float4*>(st + j);
+                        const float4 Y = *reinterpret_cast<const float4*>(st + CD_TILE + j);
+                        const float4 Z = *reinterpret_cast<const float4*>(st + 2 * CD_TILE + j);
+                        cd_four_candidates<R, VAR>(qx, qy, qz, rowmin, X, Y, Z, col + j, lane);
+                    }
+                }
+                __syncthreads();  // stage drained by every warp; this tile's column atomics are done
+                if (tid == 0 && t + 2 < ntiles) {
+                    fence_proxy_async();
+                    issue(t + 2);
+                }
+            }
+            const int nvalid = npts - i0;
+#pragma unroll
+            for (int k = 0; k < R; ++k)
+                if (k < nvalid) total += rowmin[k];
+        }
+        // cloud pair (s, r) complete: fold this half's column minima, reset them for the next r
+        for (int j = ht; j < npad; j += CD_HALF) {
+            if (j < npts) total += __uint_as_float(mycol[j]);
+            mycol[j] = CD_INF_BITS;
+        }
+        total = warp_sum(total);
+        if (lane == 0) red[half * 4 + hw] = total;
+        __syncthreads();
+        if (ht == 0 && s_valid) {
+            const float* rr = red + half * 4;
+            out[(size_t)s * ld_out + r] = (rr[0] + rr[1] + rr[2] + rr[3]) * inv_n;
+        }
+    }
+}
+
+template <int NH, int VAR = 0>
+constexpr size_t cd_smem_bytes(int npad) {
+    return (size_t)(2 * ((VAR & CDV_AOS) ? 4 : 3) * CD_TILE + NH * (size_t)npad + NH * 4) * 4 + 2 * sizeof(uint64_t);
+}
+
+}  // namespace pdgn
