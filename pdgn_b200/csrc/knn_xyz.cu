@@ -6,19 +6,22 @@
 // ascending (d2, index), d2 by the native FMUL/FFMA/FFMA chain (d2_xyz), NaN/+inf distances never selected,
 // missing neighbours reported as idx 0 / dist2 +inf.
 //
-// Fast path (knn_fast_kernel), FP32 SIMT, two scans of the candidate set per query, no sorted structure in the
-// hot loops:
-//   pass 1  every thread keeps KF_R queries in registers and scans the candidates, staged in shared memory as
-//           SoA planes (warp-broadcast LDS.128 = 4 candidates per plane per load).  It only tracks the MINIMUM
-//           distance inside each of G contiguous candidate groups (FMNMX3, 0.5 instr per pair).
-//   bound   the k-th smallest of the G group minima is an upper bound tau on the k-th nearest distance (k
-//           distinct groups each hold a candidate <= tau).  It is found with a register-resident bitonic
-//           sorting network over the G minima (FMNMX only, branch free, all lanes busy).
-//   pass 2  rescan; candidates with d2 <= tau (typically ~1.5 k of them) are appended, in index order, to a small
-//           per-query queue of 16-bit indices in shared memory (predicated STS).
-//   final   each thread insertion-sorts its queue by (d2, index) into a k-entry list and writes it out.  A queue
-//           overflow (adversarial ties / clustering) makes that thread redo its query with the exact generic
-//           scan, so the result is always exact.
+// Fast path (knn_select_kernel): no sorted structure and no divergent insertion in the hot loop.
+//   pass 1  (lane = query) every lane scans all candidates, staged in shared memory as SoA planes and read as
+//           warp-broadcast LDS.128 (4 candidates per plane per load), and records only MINIMA: one per subgroup of
+//           `ss` consecutive candidates (stored as bf16 rounded DOWN) and one per group of `gsz` subgroups (bf16
+//           rounded UP).  6 FMA-pipe + 0.5 FMNMX3 instructions per point pair.
+//   bound   tau = k-th smallest group minimum, from a register-resident bitonic network over the G group minima
+//           (branch free, lane = query).  k distinct groups each hold a candidate <= tau, so tau bounds the k-th
+//           nearest distance from above; rounding up keeps it a bound, rounding the subgroup minima down keeps the
+//           filter below free of false negatives.
+//   pass 2  (warp = query, 32 queries in turn) the warp ballots which subgroups can hold a survivor
+//           (subgroup minimum <= tau: about k of them), rescans only those candidates (32 per step, one per lane),
+//           compacts the survivors d2 <= tau in index order with ballot/popc, and ranks them: every lane counts how
+//           many survivors precede its own in (d2, index) order and, if that rank is < k, stores straight into
+//           idx[rank].  Warp-uniform control flow throughout.
+//   A survivor overflow (adversarial ties / clustering / fewer than k finite candidates) sends that one query to
+//   an exact serial scan, so the result is always exact.
 // Generic path (knn_generic_kernel): any k <= 128, any n; threshold-guarded insertion into a shared-memory list.
 #include "common.cuh"
 
@@ -73,12 +76,11 @@ __global__ void __launch_bounds__(KG_T) knn_generic_kernel(const float* __restri
 }
 
 // =====================================================================================================
-// fast two-pass kernel
+// fast kernel: minima scan + warp-cooperative selection
 // =====================================================================================================
-constexpr int KF_T = 128;            // threads per CTA
-constexpr int KF_R = 2;              // queries per thread
-constexpr int KF_Q = KF_T * KF_R;    // queries per CTA
-constexpr int KF_TILE = 2048;        // candidate capacity of the shared tile
+constexpr int KS_TILE = 2048;   // candidate capacity of the shared tile
+constexpr int KS_NSUB = 128;    // subgroup-minimum rows per query
+constexpr int KS_SCAP = 128;    // survivor capacity per query
 
 template <int N>
 __device__ __forceinline__ void bitonic_sort_regs(float (&v)[N]) {
@@ -101,191 +103,236 @@ __device__ __forceinline__ void bitonic_sort_regs(float (&v)[N]) {
 }
 
 // Cooperative load of candidates [j0, j0+cnt) of one batch element, AoS global -> SoA shared, tail padded to a
-// multiple of 4 with NaN (a NaN distance is never a minimum and never <= tau).
-__device__ __forceinline__ void kf_load_tile(float* tile, const float* __restrict__ pb, int j0, int cnt, int t) {
-    for (int e = t; e < cnt * 3; e += KF_T) {
+// multiple of 4 with NaN (a NaN distance is never a minimum).
+template <int THREADS>
+__device__ __forceinline__ void ks_load_tile(float* tile, const float* __restrict__ pb, int j0, int cnt, int t) {
+    for (int e = t; e < cnt * 3; e += THREADS) {
         const int j = e / 3, c = e - j * 3;
-        tile[c * KF_TILE + j] = pb[(size_t)j0 * 3 + e];
+        tile[c * KS_TILE + j] = pb[(size_t)j0 * 3 + e];
     }
     const int cnt4 = (cnt + 3) & ~3;
     if (t < cnt4 - cnt) {
         const float nanv = __int_as_float(0x7fc00000);
         tile[cnt + t] = nanv;
-        tile[KF_TILE + cnt + t] = nanv;
-        tile[2 * KF_TILE + cnt + t] = nanv;
+        tile[KS_TILE + cnt + t] = nanv;
+        tile[2 * KS_TILE + cnt + t] = nanv;
     }
 }
 
-template <int G, int QCAP>
-__global__ void __launch_bounds__(KF_T) knn_fast_kernel(const float* __restrict__ xyz, const float* __restrict__ new_xyz, int n,
-                                                       int m, int k, int gs, int* __restrict__ idx, float* __restrict__ dist2) {
+// per-warp shared block
+template <int G>
+struct KsWarp {
+    unsigned short sub[KS_NSUB][32];  // [subgroup][(query + subgroup) & 31]  bf16, rounded down  (swizzled: both the
+                                      //   lane=query writes and the lane=subgroup reads are bank-conflict free)
+    unsigned short grp[G][32];        // [group][query]  bf16, rounded up
+    float sd[KS_SCAP];                // survivors of the query being selected: distance ...
+    int si[KS_SCAP];                  // ... and candidate index, in index order
+    unsigned short plist[KS_NSUB];    // subgroups that may hold survivors
+};
+
+template <int G, int NWARPS>
+__global__ void __launch_bounds__(NWARPS * 32) knn_select_kernel(const float* __restrict__ xyz, const float* __restrict__ new_xyz,
+                                                                int n, int m, int k, int log2ss, int gsz, int* __restrict__ idx,
+                                                                float* __restrict__ dist2) {
+    constexpr int THREADS = NWARPS * 32;
     extern __shared__ __align__(16) unsigned char smem_raw[];
-    float* tile = reinterpret_cast<float*>(smem_raw);                         // [3][KF_TILE]
-    unsigned short* queue = reinterpret_cast<unsigned short*>(tile + 3 * KF_TILE);  // [QCAP][KF_Q]
-    float* gm = reinterpret_cast<float*>(queue + (size_t)QCAP * KF_Q);         // [G][KF_Q]   (pass 1 / bound)
-    float* ld = gm;                                                           // [k][KF_Q]   (final; overlays gm)
-    int* li = reinterpret_cast<int*>(ld + (size_t)k * KF_Q);                   // [k][KF_Q]
+    float* tile = reinterpret_cast<float*>(smem_raw);  // [3][KS_TILE]
+    KsWarp<G>* wsm = reinterpret_cast<KsWarp<G>*>(tile + 3 * KS_TILE) + (threadIdx.x >> 5);
 
-    const int bz = blockIdx.y, t = threadIdx.x;
-    const int qbase = blockIdx.x * KF_Q;
+    const int bz = blockIdx.y, t = threadIdx.x, lane = t & 31, warp = t >> 5;
+    const int ss = 1 << log2ss;
+    const int nsub = (n + ss - 1) >> log2ss;          // <= KS_NSUB
+    const int ng = (nsub + gsz - 1) / gsz;            // <= G
     const float* pb = xyz + (size_t)bz * n * 3;
-    float qx[KF_R], qy[KF_R], qz[KF_R];
-#pragma unroll
-    for (int r = 0; r < KF_R; ++r) {
-        const int q = min(qbase + r * KF_T + t, m - 1);  // slot r*KF_T + t  (lane-contiguous shared columns)
-        const float* qp = new_xyz + ((size_t)bz * m + q) * 3;
-        qx[r] = qp[0]; qy[r] = qp[1]; qz[r] = qp[2];
-    }
-    const int ng = (n + gs - 1) / gs;             // non-empty groups (<= G)
-    const int tile_cands = (KF_TILE / gs) * gs;   // whole groups per tile
+    const int q0 = blockIdx.x * THREADS + warp * 32;  // first query of this warp
+    const int qmine = min(q0 + lane, m - 1);
+    const float* qp = new_xyz + ((size_t)bz * m + qmine) * 3;
+    const float qx = qp[0], qy = qp[1], qz = qp[2];
 
-    // ---------------- pass 1: group minima
-    for (int g = ng; g < G; ++g) {
-#pragma unroll
-        for (int r = 0; r < KF_R; ++r) gm[g * KF_Q + r * KF_T + t] = kInf;
-    }
-    for (int j0 = 0; j0 < n; j0 += tile_cands) {
-        const int cnt = min(tile_cands, n - j0);
-        __syncthreads();
-        kf_load_tile(tile, pb, j0, cnt, t);
-        __syncthreads();
-        for (int gj = 0; gj < cnt; gj += gs) {
-            const int gend = min(cnt, gj + gs);
-            float mn[KF_R];
-#pragma unroll
-            for (int r = 0; r < KF_R; ++r) mn[r] = kInf;
-#pragma unroll 2
-            for (int j = gj; j < gend; j += 4) {
-                const float4 X = *reinterpret_cast<const float4*>(tile + j);
-                const float4 Y = *reinterpret_cast<const float4*>(tile + KF_TILE + j);
-                const float4 Z = *reinterpret_cast<const float4*>(tile + 2 * KF_TILE + j);
-#pragma unroll
-                for (int r = 0; r < KF_R; ++r) {
-                    const float d0 = d2_xyz(qx[r], qy[r], qz[r], X.x, Y.x, Z.x), d1 = d2_xyz(qx[r], qy[r], qz[r], X.y, Y.y, Z.y);
-                    const float d2 = d2_xyz(qx[r], qy[r], qz[r], X.z, Y.z, Z.z), d3 = d2_xyz(qx[r], qy[r], qz[r], X.w, Y.w, Z.w);
-                    mn[r] = min3(min3(mn[r], d0, d1), d2, d3);
+    for (int g = ng; g < G; ++g) wsm->grp[g][lane] = 0x7f80;  // +inf for groups that do not exist
+
+    // ---------------- pass 1: subgroup / group minima (lane = query)
+    {
+        float gmn = kInf;
+        for (int j0 = 0; j0 < n; j0 += KS_TILE) {
+            const int cnt = min(KS_TILE, n - j0);
+            __syncthreads();
+            ks_load_tile<THREADS>(tile, pb, j0, cnt, t);
+            __syncthreads();
+            const int sg0 = j0 >> log2ss;
+            const int nsg = (cnt + ss - 1) >> log2ss;
+            for (int sl = 0; sl < nsg; ++sl) {
+                const int jb = sl << log2ss, je = min(cnt, jb + ss);
+                float mn = kInf;
+#pragma unroll 4
+                for (int j = jb; j < je; j += 4) {
+                    const float4 X = *reinterpret_cast<const float4*>(tile + j);
+                    const float4 Y = *reinterpret_cast<const float4*>(tile + KS_TILE + j);
+                    const float4 Z = *reinterpret_cast<const float4*>(tile + 2 * KS_TILE + j);
+                    const float d0 = d2_xyz(qx, qy, qz, X.x, Y.x, Z.x), d1 = d2_xyz(qx, qy, qz, X.y, Y.y, Z.y);
+                    const float d2 = d2_xyz(qx, qy, qz, X.z, Y.z, Z.z), d3 = d2_xyz(qx, qy, qz, X.w, Y.w, Z.w);
+                    mn = min3(min3(mn, d0, d1), d2, d3);
+                }
+                const int sg = sg0 + sl;
+                wsm->sub[sg][(lane + sg) & 31] = (unsigned short)(__float_as_uint(mn) >> 16);  // toward zero = down (mn >= 0)
+                gmn = fminf(gmn, mn);
+                if ((sg + 1) % gsz == 0 || sg == nsub - 1) {
+                    const unsigned u = __float_as_uint(gmn);
+                    wsm->grp[sg / gsz][lane] = (unsigned short)((u + 0xffffu) >> 16);         // up
+                    gmn = kInf;
                 }
             }
-            const int g = (j0 + gj) / gs;
-#pragma unroll
-            for (int r = 0; r < KF_R; ++r) gm[g * KF_Q + r * KF_T + t] = mn[r];
         }
     }
 
-    // ---------------- bound: tau = k-th smallest group minimum (own columns only: no barrier needed)
-    float tau[KF_R];
-#pragma unroll
-    for (int r = 0; r < KF_R; ++r) {
+    // ---------------- bound: tau = k-th smallest group minimum (own column only)
+    float tau;
+    {
         float v[G];
 #pragma unroll
-        for (int g = 0; g < G; ++g) v[g] = gm[g * KF_Q + r * KF_T + t];
+        for (int g = 0; g < G; ++g) v[g] = __uint_as_float((unsigned)wsm->grp[g][lane] << 16);
         bitonic_sort_regs<G>(v);
-        float tv = kInf;
+        // v ascending => v[k-1] = max(v[0..k-1]); written as a predicated max so that the compiler cannot turn it into
+        // a dynamically indexed (local-memory) array access
+        tau = 0.f;
 #pragma unroll
-        for (int g = 0; g < G; ++g)
-            if (g == k - 1) tv = v[g];
-        tau[r] = tv;
+        for (int g = 0; g < G; ++g) tau = (g < k) ? fmaxf(tau, v[g]) : tau;
     }
+    __syncwarp();
 
-    // ---------------- pass 2: append every candidate with d2 <= tau (index order)
-    int cnt_q[KF_R];
+    // ---------------- pass 2: warp-cooperative selection, one query at a time
+    const unsigned lt = (1u << lane) - 1u;
+    const int nq = min(32, m - q0);
+    for (int qi = 0; qi < nq; ++qi) {
+        const float tq = __shfl_sync(kFull, tau, qi);
+        const float ax = __shfl_sync(kFull, qx, qi), ay = __shfl_sync(kFull, qy, qi), az = __shfl_sync(kFull, qz, qi);
+        // subgroups whose (rounded-down) minimum is <= tau, in ascending order
+        int npass = 0;
 #pragma unroll
-    for (int r = 0; r < KF_R; ++r) cnt_q[r] = 0;
-    const bool single_tile = n <= tile_cands;
-    for (int j0 = 0; j0 < n; j0 += tile_cands) {
-        const int cnt = min(tile_cands, n - j0);
-        if (!single_tile) {
-            __syncthreads();
-            kf_load_tile(tile, pb, j0, cnt, t);
-            __syncthreads();
+        for (int i = 0; i < KS_NSUB / 32; ++i) {
+            const int sg = lane + 32 * i;
+            bool p = false;
+            if (sg < nsub) p = __uint_as_float((unsigned)wsm->sub[sg][(qi + sg) & 31] << 16) <= tq;
+            const unsigned mask = __ballot_sync(kFull, p);
+            if (p) wsm->plist[npass + __popc(mask & lt)] = (unsigned short)sg;
+            npass += __popc(mask);
         }
-        const int cnt4 = (cnt + 3) & ~3;
-#pragma unroll 2
-        for (int j = 0; j < cnt4; j += 4) {
-            const float4 X = *reinterpret_cast<const float4*>(tile + j);
-            const float4 Y = *reinterpret_cast<const float4*>(tile + KF_TILE + j);
-            const float4 Z = *reinterpret_cast<const float4*>(tile + 2 * KF_TILE + j);
-#pragma unroll
-            for (int r = 0; r < KF_R; ++r) {
-                float d[4];
-                d[0] = d2_xyz(qx[r], qy[r], qz[r], X.x, Y.x, Z.x);
-                d[1] = d2_xyz(qx[r], qy[r], qz[r], X.y, Y.y, Z.y);
-                d[2] = d2_xyz(qx[r], qy[r], qz[r], X.z, Y.z, Z.z);
-                d[3] = d2_xyz(qx[r], qy[r], qz[r], X.w, Y.w, Z.w);
-#pragma unroll
-                for (int u = 0; u < 4; ++u) {
-                    if (d[u] <= tau[r]) {
-                        if (cnt_q[r] < QCAP) queue[cnt_q[r] * KF_Q + r * KF_T + t] = (unsigned short)(j0 + j + u);
-                        ++cnt_q[r];
-                    }
+        __syncwarp();
+        // rescan those subgroups, 32 candidates per step; survivors compacted in index order
+        const int total = npass << log2ss;
+        int nsurv = 0;
+        for (int p0 = 0; p0 < total; p0 += 32) {
+            const int p = p0 + lane;
+            bool ok = p < total;
+            const int sg = wsm->plist[ok ? (p >> log2ss) : 0];
+            const int j = (sg << log2ss) + (p & (ss - 1));
+            ok = ok && j < n;
+            float d = kInf;
+            if (ok) {
+                const float* c = pb + (size_t)j * 3;
+                d = d2_xyz(ax, ay, az, __ldg(c), __ldg(c + 1), __ldg(c + 2));
+            }
+            const bool keep = ok && d <= tq && d < kInf;
+            const unsigned mask = __ballot_sync(kFull, keep);
+            const int pos = nsurv + __popc(mask & lt);
+            if (keep && pos < KS_SCAP) {
+                wsm->sd[pos] = d;
+                wsm->si[pos] = j;
+            }
+            nsurv += __popc(mask);
+        }
+        __syncwarp();
+        int* oi = idx + ((size_t)bz * m + q0 + qi) * k;
+        float* od = dist2 ? dist2 + ((size_t)bz * m + q0 + qi) * k : nullptr;
+        if (nsurv <= KS_SCAP) {
+            // rank = number of survivors that precede mine in (d2, index) order; positions are in index order
+            for (int e0 = 0; e0 < nsurv; e0 += 32) {
+                const int e = e0 + lane;
+                const bool have = e < nsurv;
+                const float de = have ? wsm->sd[e] : kInf;
+                int rank = 0;
+                int f = 0;
+                for (; f + 4 <= nsurv; f += 4) {
+                    const float4 df = *reinterpret_cast<const float4*>(wsm->sd + f);
+                    rank += (df.x < de || (df.x == de && f < e)) ? 1 : 0;
+                    rank += (df.y < de || (df.y == de && f + 1 < e)) ? 1 : 0;
+                    rank += (df.z < de || (df.z == de && f + 2 < e)) ? 1 : 0;
+                    rank += (df.w < de || (df.w == de && f + 3 < e)) ? 1 : 0;
+                }
+                for (; f < nsurv; ++f) {
+                    const float df = wsm->sd[f];
+                    rank += (df < de || (df == de && f < e)) ? 1 : 0;
+                }
+                if (have && rank < k) {
+                    oi[rank] = wsm->si[e];
+                    if (od) od[rank] = de;
                 }
             }
-        }
-    }
-    __syncthreads();  // every thread is done with gm before the lists (which overlay it) are written
-
-    // ---------------- final: exact (d2, index) order among the survivors
-#pragma unroll
-    for (int r = 0; r < KF_R; ++r) {
-        const int col = r * KF_T + t;
-        for (int e = 0; e < k; ++e) {
-            ld[e * KF_Q + col] = kInf;
-            li[e * KF_Q + col] = 0;
-        }
-        float thr = kInf;
-        if (cnt_q[r] <= QCAP) {
-            for (int e = 0; e < cnt_q[r]; ++e) {
-                const int j = queue[e * KF_Q + col];
-                const float* p = pb + (size_t)j * 3;
-                const float d = d2_xyz(qx[r], qy[r], qz[r], __ldg(p), __ldg(p + 1), __ldg(p + 2));
-                if (d < thr) {
-                    list_insert(ld, li, KF_Q, col, k, d, j);
-                    thr = ld[(k - 1) * KF_Q + col];
-                }
+            for (int e = nsurv + lane; e < k; e += 32) {  // fewer than k finite candidates
+                oi[e] = 0;
+                if (od) od[e] = kInf;
             }
-        } else {  // queue overflow: exact rescan of the whole candidate set for this query only
-            for (int j = 0; j < n; ++j) {
-                const float* p = pb + (size_t)j * 3;
-                const float d = d2_xyz(qx[r], qy[r], qz[r], __ldg(p), __ldg(p + 1), __ldg(p + 2));
-                if (d < thr) {
-                    list_insert(ld, li, KF_Q, col, k, d, j);
-                    thr = ld[(k - 1) * KF_Q + col];
-                }
-            }
-        }
-        const int q = qbase + col;
-        if (q < m) {
-            const size_t o = ((size_t)bz * m + q) * k;
+        } else if (lane == 0) {
+            // survivor overflow: exact serial scan of every candidate for this query (sd/si double as the k-entry list)
             for (int e = 0; e < k; ++e) {
-                idx[o + e] = li[e * KF_Q + col];
-                if (dist2) dist2[o + e] = ld[e * KF_Q + col];
+                wsm->sd[e] = kInf;
+                wsm->si[e] = 0;
+            }
+            float thr = kInf;
+            for (int j = 0; j < n; ++j) {
+                const float* c = pb + (size_t)j * 3;
+                const float d = d2_xyz(ax, ay, az, __ldg(c), __ldg(c + 1), __ldg(c + 2));
+                if (d < thr) {
+                    list_insert(wsm->sd, wsm->si, 1, 0, k, d, j);
+                    thr = wsm->sd[k - 1];
+                }
+            }
+            for (int e = 0; e < k; ++e) {
+                oi[e] = wsm->si[e];
+                if (od) od[e] = wsm->sd[e];
             }
         }
+        __syncwarp();
     }
 }
 
-template <int G, int QCAP>
-static int launch_fast(const float* xyz, const float* new_xyz, int b, int n, int m, int k, int gs, int* idx, float* dist2,
-                       cudaStream_t st) {
-    const size_t overlay = (size_t)KF_Q * 4 * (size_t)max(G, 2 * k);
-    const size_t smem = (size_t)3 * KF_TILE * 4 + (size_t)QCAP * KF_Q * 2 + overlay;
-    PDGN_CUDA(cudaFuncSetAttribute(knn_fast_kernel<G, QCAP>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    dim3 grid((m + KF_Q - 1) / KF_Q, b);
-    knn_fast_kernel<G, QCAP><<<grid, KF_T, smem, st>>>(xyz, new_xyz, n, m, k, gs, idx, dist2);
+template <int G, int NWARPS>
+static int launch_select(const float* xyz, const float* new_xyz, int b, int n, int m, int k, int log2ss, int gsz, int* idx,
+                         float* dist2, cudaStream_t st) {
+    const size_t smem = (size_t)3 * KS_TILE * 4 + (size_t)NWARPS * sizeof(KsWarp<G>);
+    PDGN_CUDA(cudaFuncSetAttribute(knn_select_kernel<G, NWARPS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    dim3 grid((m + NWARPS * 32 - 1) / (NWARPS * 32), b);
+    knn_select_kernel<G, NWARPS><<<grid, NWARPS * 32, smem, st>>>(xyz, new_xyz, n, m, k, log2ss, gsz, idx, dist2);
     PDGN_CHECK_LAUNCH();
     return PDGN_OK;
 }
 
-static inline int group_size(int n, int G) { return max(4, ((n + G - 1) / G + 3) & ~3); }
+// Subgroup size (power of two >= 4 covering n with at most KS_NSUB subgroups) and subgroups per group such that the
+// number of groups is in [k, G].  Returns false when no such split exists (tiny n or large k): generic kernel.
+static bool select_plan(int n, int k, int G, int* log2ss, int* gsz) {
+    int l = 2;
+    while (((n + (1 << l) - 1) >> l) > KS_NSUB) ++l;
+    if ((1 << l) > KS_TILE) return false;
+    const int nsub = (n + (1 << l) - 1) >> l;
+    for (int g = 4; g >= 1; g >>= 1) {
+        const int ng = (nsub + g - 1) / g;
+        if (ng >= k && ng <= G) {
+            *log2ss = l;
+            *gsz = g;
+            return true;
+        }
+    }
+    return false;
+}
 
 static int knn_dispatch(const float* xyz, const float* new_xyz, int b, int n, int m, int k, int* idx, float* dist2, cudaStream_t st) {
-    // Fast path needs: >= k non-empty groups (else tau = +inf), 16-bit candidate indices, whole groups per tile.
-    if (n <= 65535) {
-        int gs = group_size(n, 32);
-        if (k <= 20 && (n + gs - 1) / gs >= k && gs <= KF_TILE) return launch_fast<32, 64>(xyz, new_xyz, b, n, m, k, gs, idx, dist2, st);
-        gs = group_size(n, 64);
-        if (k <= 40 && (n + gs - 1) / gs >= k && gs <= KF_TILE) return launch_fast<64, 128>(xyz, new_xyz, b, n, m, k, gs, idx, dist2, st);
+    int log2ss = 0, gsz = 0;
+    // k <= 24 of 32 groups / k <= 48 of 64 groups keeps the expected survivor count (~G/(G-k) * k-ish) well under KS_SCAP
+    if (k <= 24 && select_plan(n, k, 32, &log2ss, &gsz)) {
+        if (m > 256) return launch_select<32, 16>(xyz, new_xyz, b, n, m, k, log2ss, gsz, idx, dist2, st);
+        return launch_select<32, 8>(xyz, new_xyz, b, n, m, k, log2ss, gsz, idx, dist2, st);
     }
+    if (k <= 48 && select_plan(n, k, 64, &log2ss, &gsz)) return launch_select<64, 8>(xyz, new_xyz, b, n, m, k, log2ss, gsz, idx, dist2, st);
     const size_t smem = (size_t)3 * KG_TILE * 4 + (size_t)k * KG_T * 8;
     PDGN_CUDA(cudaFuncSetAttribute(knn_generic_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     dim3 grid((m + KG_T - 1) / KG_T, b);

@@ -41,6 +41,11 @@ KNN_CASES = [
     ("U-small-n-generic", clouds_uniform, 2, 40, 40, 20),
     ("U-n-lt-k", clouds_uniform, 2, 5, 9, 8),
     ("U-train-256x2048", clouds_uniform, 3, 2048, 256, 20),
+    ("S-train-256x256", clouds_sphere, 3, 256, 256, 20),
+    ("U-n100-k20", clouds_uniform, 2, 100, 100, 20),
+    ("U-n6000-k20", clouds_uniform, 1, 6000, 700, 20),
+    ("S-16384-k32", clouds_sphere, 1, 16384, 1000, 32),
+    ("T-ties-2048-k20", clouds_ties, 2, 2048, 600, 20),
 ]
 
 
