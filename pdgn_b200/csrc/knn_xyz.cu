@@ -122,12 +122,12 @@ __device__ __forceinline__ void ks_load_tile(float* tile, const float* __restric
 // per-warp shared block
 template <int G>
 struct KsWarp {
-    unsigned short sub[KS_NSUB][32];  // [subgroup][(query + subgroup) & 31]  bf16, rounded down  (swizzled: both the
-                                      //   lane=query writes and the lane=subgroup reads are bank-conflict free)
-    unsigned short grp[G][32];        // [group][query]  bf16, rounded up
-    float sd[KS_SCAP];                // survivors of the query being selected: distance ...
-    int si[KS_SCAP];                  // ... and candidate index, in index order
-    unsigned short plist[KS_NSUB];    // subgroups that may hold survivors
+    unsigned short sub[KS_NSUB][32];   // [subgroup][(query + subgroup) & 31]  bf16, rounded down  (swizzled: both the
+                                       //   lane=query writes and the lane=subgroup reads are bank-conflict free)
+    unsigned short grp[G][32];         // [group][query]  bf16, rounded up
+    unsigned long long key[KS_SCAP];   // survivors of the query being selected: (d2 bits << 32) | position, index order
+    int si[KS_SCAP];                   // ... and their candidate indices
+    unsigned short plist[KS_NSUB];     // subgroups that may hold survivors
 };
 
 template <int G, int NWARPS>
@@ -154,15 +154,17 @@ __global__ void __launch_bounds__(NWARPS * 32) knn_select_kernel(const float* __
     // ---------------- pass 1: subgroup / group minima (lane = query)
     {
         float gmn = kInf;
+        int gleft = gsz;                                   // subgroups left in the current group
+        unsigned short* subrow = &wsm->sub[0][0];          // row of the current subgroup
+        unsigned short* grow = &wsm->grp[0][lane];
+        int col = lane;                                    // (lane + sg) & 31
         for (int j0 = 0; j0 < n; j0 += KS_TILE) {
             const int cnt = min(KS_TILE, n - j0);
             __syncthreads();
             ks_load_tile<THREADS>(tile, pb, j0, cnt, t);
             __syncthreads();
-            const int sg0 = j0 >> log2ss;
-            const int nsg = (cnt + ss - 1) >> log2ss;
-            for (int sl = 0; sl < nsg; ++sl) {
-                const int jb = sl << log2ss, je = min(cnt, jb + ss);
+            for (int jb = 0; jb < cnt; jb += ss) {
+                const int je = min(cnt, jb + ss);
                 float mn = kInf;
 #pragma unroll 4
                 for (int j = jb; j < je; j += 4) {
@@ -173,16 +175,19 @@ __global__ void __launch_bounds__(NWARPS * 32) knn_select_kernel(const float* __
                     const float d2 = d2_xyz(qx, qy, qz, X.z, Y.z, Z.z), d3 = d2_xyz(qx, qy, qz, X.w, Y.w, Z.w);
                     mn = min3(min3(mn, d0, d1), d2, d3);
                 }
-                const int sg = sg0 + sl;
-                wsm->sub[sg][(lane + sg) & 31] = (unsigned short)(__float_as_uint(mn) >> 16);  // toward zero = down (mn >= 0)
+                subrow[col] = (unsigned short)(__float_as_uint(mn) >> 16);   // toward zero = down (mn >= 0)
+                subrow += 32;
+                col = (col + 1) & 31;
                 gmn = fminf(gmn, mn);
-                if ((sg + 1) % gsz == 0 || sg == nsub - 1) {
-                    const unsigned u = __float_as_uint(gmn);
-                    wsm->grp[sg / gsz][lane] = (unsigned short)((u + 0xffffu) >> 16);         // up
+                if (--gleft == 0) {
+                    *grow = (unsigned short)((__float_as_uint(gmn) + 0xffffu) >> 16);  // up
+                    grow += 32;
                     gmn = kInf;
+                    gleft = gsz;
                 }
             }
         }
+        if (gleft != gsz) *grow = (unsigned short)((__float_as_uint(gmn) + 0xffffu) >> 16);  // ragged last group
     }
 
     // ---------------- bound: tau = k-th smallest group minimum (own column only)
@@ -203,6 +208,7 @@ __global__ void __launch_bounds__(NWARPS * 32) knn_select_kernel(const float* __
     // ---------------- pass 2: warp-cooperative selection, one query at a time
     const unsigned lt = (1u << lane) - 1u;
     const int nq = min(32, m - q0);
+    const bool resident = n <= KS_TILE;  // the single tile of pass 1 is still in shared memory
     for (int qi = 0; qi < nq; ++qi) {
         const float tq = __shfl_sync(kFull, tau, qi);
         const float ax = __shfl_sync(kFull, qx, qi), ay = __shfl_sync(kFull, qy, qi), az = __shfl_sync(kFull, qz, qi);
@@ -218,54 +224,76 @@ __global__ void __launch_bounds__(NWARPS * 32) knn_select_kernel(const float* __
             npass += __popc(mask);
         }
         __syncwarp();
-        // rescan those subgroups, 32 candidates per step; survivors compacted in index order
+        // rescan those subgroups: 4 consecutive candidates per lane, 128 per step; survivors compacted in index order
         const int total = npass << log2ss;
         int nsurv = 0;
-        for (int p0 = 0; p0 < total; p0 += 32) {
-            const int p = p0 + lane;
-            bool ok = p < total;
+        for (int p0 = 0; p0 < total; p0 += 128) {
+            const int p = p0 + 4 * lane;
+            const bool ok = p < total;
             const int sg = wsm->plist[ok ? (p >> log2ss) : 0];
-            const int j = (sg << log2ss) + (p & (ss - 1));
-            ok = ok && j < n;
-            float d = kInf;
-            if (ok) {
-                const float* c = pb + (size_t)j * 3;
-                d = d2_xyz(ax, ay, az, __ldg(c), __ldg(c + 1), __ldg(c + 2));
+            const int j = (sg << log2ss) + (p & (ss - 1));  // multiple of 4; j..j+3 stay inside the subgroup
+            float d[4];
+            if (resident) {
+                const float4 X = *reinterpret_cast<const float4*>(tile + j);
+                const float4 Y = *reinterpret_cast<const float4*>(tile + KS_TILE + j);
+                const float4 Z = *reinterpret_cast<const float4*>(tile + 2 * KS_TILE + j);
+                d[0] = d2_xyz(ax, ay, az, X.x, Y.x, Z.x);
+                d[1] = d2_xyz(ax, ay, az, X.y, Y.y, Z.y);
+                d[2] = d2_xyz(ax, ay, az, X.z, Y.z, Z.z);
+                d[3] = d2_xyz(ax, ay, az, X.w, Y.w, Z.w);
+            } else {
+#pragma unroll
+                for (int u = 0; u < 4; ++u) {
+                    d[u] = kInf;
+                    if (ok && j + u < n) {
+                        const float* c = pb + (size_t)(j + u) * 3;
+                        d[u] = d2_xyz(ax, ay, az, __ldg(c), __ldg(c + 1), __ldg(c + 2));
+                    }
+                }
             }
-            const bool keep = ok && d <= tq && d < kInf;
-            const unsigned mask = __ballot_sync(kFull, keep);
-            const int pos = nsurv + __popc(mask & lt);
-            if (keep && pos < KS_SCAP) {
-                wsm->sd[pos] = d;
-                wsm->si[pos] = j;
+            bool keep[4];
+            int below = 0, mine = 0;  // survivors in lower lanes / in this lane so far
+            unsigned all = 0;
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+                keep[u] = ok && j + u < n && d[u] <= tq && d[u] < kInf;  // NaN and +inf never survive; j+u >= n: ragged subgroup
+                const unsigned mask = __ballot_sync(kFull, keep[u]);
+                below += __popc(mask & lt);
+                all += __popc(mask);
             }
-            nsurv += __popc(mask);
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+                if (keep[u]) {
+                    const int pos = nsurv + below + mine;
+                    if (pos < KS_SCAP) {
+                        wsm->key[pos] = ((unsigned long long)__float_as_uint(d[u]) << 32) | (unsigned)pos;
+                        wsm->si[pos] = j + u;
+                    }
+                    ++mine;
+                }
+            }
+            nsurv += all;
         }
         __syncwarp();
         int* oi = idx + ((size_t)bz * m + q0 + qi) * k;
         float* od = dist2 ? dist2 + ((size_t)bz * m + q0 + qi) * k : nullptr;
         if (nsurv <= KS_SCAP) {
-            // rank = number of survivors that precede mine in (d2, index) order; positions are in index order
+            // rank = number of survivors whose (d2, position) key is smaller; positions follow the candidate index
             for (int e0 = 0; e0 < nsurv; e0 += 32) {
                 const int e = e0 + lane;
                 const bool have = e < nsurv;
-                const float de = have ? wsm->sd[e] : kInf;
+                const unsigned long long ke = have ? wsm->key[e] : ~0ull;
                 int rank = 0;
                 int f = 0;
-                for (; f + 4 <= nsurv; f += 4) {
-                    const float4 df = *reinterpret_cast<const float4*>(wsm->sd + f);
-                    rank += (df.x < de || (df.x == de && f < e)) ? 1 : 0;
-                    rank += (df.y < de || (df.y == de && f + 1 < e)) ? 1 : 0;
-                    rank += (df.z < de || (df.z == de && f + 2 < e)) ? 1 : 0;
-                    rank += (df.w < de || (df.w == de && f + 3 < e)) ? 1 : 0;
+                for (; f + 2 <= nsurv; f += 2) {
+                    const ulonglong2 kf = *reinterpret_cast<const ulonglong2*>(wsm->key + f);
+                    rank += (kf.x < ke) ? 1 : 0;
+                    rank += (kf.y < ke) ? 1 : 0;
                 }
-                for (; f < nsurv; ++f) {
-                    const float df = wsm->sd[f];
-                    rank += (df < de || (df == de && f < e)) ? 1 : 0;
-                }
+                if (f < nsurv) rank += (wsm->key[f] < ke) ? 1 : 0;
                 if (have && rank < k) {
                     oi[rank] = wsm->si[e];
-                    if (od) od[rank] = de;
+                    if (od) od[rank] = __uint_as_float((unsigned)(ke >> 32));
                 }
             }
             for (int e = nsurv + lane; e < k; e += 32) {  // fewer than k finite candidates
@@ -273,9 +301,10 @@ __global__ void __launch_bounds__(NWARPS * 32) knn_select_kernel(const float* __
                 if (od) od[e] = kInf;
             }
         } else if (lane == 0) {
-            // survivor overflow: exact serial scan of every candidate for this query (sd/si double as the k-entry list)
+            // survivor overflow: exact serial scan of every candidate for this query (key/si memory doubles as the list)
+            float* ldl = reinterpret_cast<float*>(wsm->key);
             for (int e = 0; e < k; ++e) {
-                wsm->sd[e] = kInf;
+                ldl[e] = kInf;
                 wsm->si[e] = 0;
             }
             float thr = kInf;
@@ -283,13 +312,13 @@ __global__ void __launch_bounds__(NWARPS * 32) knn_select_kernel(const float* __
                 const float* c = pb + (size_t)j * 3;
                 const float d = d2_xyz(ax, ay, az, __ldg(c), __ldg(c + 1), __ldg(c + 2));
                 if (d < thr) {
-                    list_insert(wsm->sd, wsm->si, 1, 0, k, d, j);
-                    thr = wsm->sd[k - 1];
+                    list_insert(ldl, wsm->si, 1, 0, k, d, j);
+                    thr = ldl[k - 1];
                 }
             }
             for (int e = 0; e < k; ++e) {
                 oi[e] = wsm->si[e];
-                if (od) od[e] = wsm->sd[e];
+                if (od) od[e] = ldl[e];
             }
         }
         __syncwarp();
