@@ -125,8 +125,8 @@ struct KsWarp {
     unsigned short sub[KS_NSUB][32];   // [subgroup][(query + subgroup) & 31]  bf16, rounded down  (swizzled: both the
                                        //   lane=query writes and the lane=subgroup reads are bank-conflict free)
     unsigned short grp[G][32];         // [group][query]  bf16, rounded up
-    unsigned long long key[KS_SCAP];   // survivors of the query being selected: (d2 bits << 32) | position, index order
-    int si[KS_SCAP];                   // ... and their candidate indices
+    unsigned long long key[KS_SCAP];   // survivors of the query being selected: (d2 bits << 32) | candidate index --
+                                       //   d2 >= 0, so unsigned order of the key == the reference's (d2, index) order
     unsigned short plist[KS_NSUB];     // subgroups that may hold survivors
 };
 
@@ -265,10 +265,7 @@ __global__ void __launch_bounds__(NWARPS * 32) knn_select_kernel(const float* __
             for (int u = 0; u < 4; ++u) {
                 if (keep[u]) {
                     const int pos = nsurv + below + mine;
-                    if (pos < KS_SCAP) {
-                        wsm->key[pos] = ((unsigned long long)__float_as_uint(d[u]) << 32) | (unsigned)pos;
-                        wsm->si[pos] = j + u;
-                    }
+                    if (pos < KS_SCAP) wsm->key[pos] = ((unsigned long long)__float_as_uint(d[u]) << 32) | (unsigned)(j + u);
                     ++mine;
                 }
             }
@@ -278,7 +275,7 @@ __global__ void __launch_bounds__(NWARPS * 32) knn_select_kernel(const float* __
         int* oi = idx + ((size_t)bz * m + q0 + qi) * k;
         float* od = dist2 ? dist2 + ((size_t)bz * m + q0 + qi) * k : nullptr;
         if (nsurv <= KS_SCAP) {
-            // rank = number of survivors whose (d2, position) key is smaller; positions follow the candidate index
+            // rank = number of survivors whose (d2, index) key is smaller
             for (int e0 = 0; e0 < nsurv; e0 += 32) {
                 const int e = e0 + lane;
                 const bool have = e < nsurv;
@@ -292,7 +289,7 @@ __global__ void __launch_bounds__(NWARPS * 32) knn_select_kernel(const float* __
                 }
                 if (f < nsurv) rank += (wsm->key[f] < ke) ? 1 : 0;
                 if (have && rank < k) {
-                    oi[rank] = wsm->si[e];
+                    oi[rank] = (int)(unsigned)ke;
                     if (od) od[rank] = __uint_as_float((unsigned)(ke >> 32));
                 }
             }
@@ -301,23 +298,24 @@ __global__ void __launch_bounds__(NWARPS * 32) knn_select_kernel(const float* __
                 if (od) od[e] = kInf;
             }
         } else if (lane == 0) {
-            // survivor overflow: exact serial scan of every candidate for this query (key/si memory doubles as the list)
+            // survivor overflow: exact serial scan of every candidate for this query (the key array doubles as the list)
             float* ldl = reinterpret_cast<float*>(wsm->key);
+            int* lil = reinterpret_cast<int*>(wsm->key) + KS_SCAP;
             for (int e = 0; e < k; ++e) {
                 ldl[e] = kInf;
-                wsm->si[e] = 0;
+                lil[e] = 0;
             }
             float thr = kInf;
             for (int j = 0; j < n; ++j) {
                 const float* c = pb + (size_t)j * 3;
                 const float d = d2_xyz(ax, ay, az, __ldg(c), __ldg(c + 1), __ldg(c + 2));
                 if (d < thr) {
-                    list_insert(ldl, wsm->si, 1, 0, k, d, j);
+                    list_insert(ldl, lil, 1, 0, k, d, j);
                     thr = ldl[k - 1];
                 }
             }
             for (int e = 0; e < k; ++e) {
-                oi[e] = wsm->si[e];
+                oi[e] = lil[e];
                 if (od) od[e] = ldl[e];
             }
         }
