@@ -106,6 +106,19 @@ def cpu_reference_rate(n_sample, n_ref, repeats=1):
     return n_sample * n_ref / dt, dt
 
 
+def traffic_from_profile(nc, world):
+    """DRAM bytes (read+write) of one cd_allpairs_kernel launch from the committed ncu --set full capture
+    (profiles/cd_allpairs_traffic.json); only valid for the configuration that was captured (1000 clouds, 1 GPU)."""
+    if nc != N_CLOUDS or world != 1:
+        return None
+    try:
+        t = json.load(open(os.path.join(ROOT, "profiles", "cd_allpairs_traffic.json")))
+        return {"bytes": t["dram_bytes_read"] + t["dram_bytes_write"], "unit": "B per launch", "source": t["source"],
+                "note": "kernel is FP32-issue bound; DRAM traffic is ~0.002 % of what HBM could move in the kernel's duration"}
+    except (OSError, ValueError, KeyError):
+        return None
+
+
 def run_reference(args, rank):
     """--impl reference: the reference's CPU path on the host cores (rank 0 only)."""
     if rank != 0:
@@ -253,7 +266,7 @@ def main():
     obs_mhz = (clocks or {}).get("sm_mhz") or sm_max_mhz
     roofline = {
         "bound": "fp32", "kernel": "cd_allpairs_kernel", "achieved": achieved_tflops, "peak": peak_tflops, "unit": "TFLOP/s",
-        "frac": achieved_tflops / peak_tflops, "traffic": None,
+        "frac": achieved_tflops / peak_tflops, "traffic": traffic_from_profile(nc, world),
         "kernel_ms": kernel_ms, "cloud_pairs_per_launch": tile_pairs,
         "definition": "achieved = cloud pairs x 2048^2 point pairs x 6 FMA-pipe instr x 2 FLOP-slots / kernel time (issue-rate "
                       "fraction == FMA-pipe utilisation, SURVEY.md 8d); peak = SMs x 128 lanes x 2 x sm_max_mhz (MEASURED_PEAKS.json)",
@@ -339,7 +352,9 @@ def bench_gathers(dev, hbm_gbs, src):
         L = lib()
         st = torch.cuda.current_stream().cuda_stream
         f_ms = _time_ms(lambda: L.pdgn_group_fwd(feat.data_ptr(), idx.data_ptr(), b, c, n, m, k, out.data_ptr(), st), 10, flush)
-        b_ms = _time_ms(lambda: L.pdgn_group_bwd(go.data_ptr(), idx.data_ptr(), b, c, n, m, k, grad.data_ptr(), st), 10, flush)
+        ws_bytes = L.pdgn_group_bwd_workspace(b, n, m, k)
+        ws = torch.empty((ws_bytes,), dtype=torch.uint8, device=dev)
+        b_ms = _time_ms(lambda: L.pdgn_group_bwd_ws(go.data_ptr(), idx.data_ptr(), b, c, n, m, k, grad.data_ptr(), ws.data_ptr(), ws_bytes, st), 10, flush)
         bytes_fwd = 4.0 * (b * c * m * k + b * m * k + b * c * n)
         res[tag] = {"fwd_ms": f_ms, "fwd_gbs": bytes_fwd / (f_ms * 1e-3) / 1e9, "fwd_frac": bytes_fwd / (f_ms * 1e-3) / 1e9 / hbm_gbs,
                     "bwd_ms": b_ms, "bwd_gbs": bytes_fwd / (b_ms * 1e-3) / 1e9, "bwd_frac": bytes_fwd / (b_ms * 1e-3) / 1e9 / hbm_gbs,

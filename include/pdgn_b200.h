@@ -58,6 +58,12 @@ int pdgn_nn3(const float *unknown, const float *known, int b, int n, int m, floa
 int pdgn_group_fwd(const float *points, const int *idx, int b, int c, int n, int m, int k, float *out, void *stream);
 int pdgn_group_bwd(const float *grad_out, const int *idx, int b, int c, int n, int m, int k, float *grad_points,
                    void *stream);
+/* Same result through a deterministic pull (inverse index built in `workspace`, pdgn_group_bwd_workspace(b,n,m,k)
+ * bytes; each target sums its contributions in ascending position order, no float atomics).  Falls back to the
+ * atomic kernel for c < 4 or rows that do not fit shared memory. */
+size_t pdgn_group_bwd_workspace(int b, int n, int m, int k);
+int pdgn_group_bwd_ws(const float *grad_out, const int *idx, int b, int c, int n, int m, int k, float *grad_points,
+                      void *workspace, size_t workspace_bytes, void *stream);
 
 /* ---- three-point interpolation and its backward -----------------------------------------------------
  * Replace interpolation_forward_cuda_launcher_fast / interpolation_backward_cuda_launcher

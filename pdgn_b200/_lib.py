@@ -23,6 +23,8 @@ SIGNATURES = {
     "pdgn_nn3": (_I, [_P, _P, _I, _I, _I, _P, _P, _P]),
     "pdgn_group_fwd": (_I, [_P, _P, _I, _I, _I, _I, _I, _P, _P]),
     "pdgn_group_bwd": (_I, [_P, _P, _I, _I, _I, _I, _I, _P, _P]),
+    "pdgn_group_bwd_workspace": (_SZ, [_I, _I, _I, _I]),
+    "pdgn_group_bwd_ws": (_I, [_P, _P, _I, _I, _I, _I, _I, _P, _P, _SZ, _P]),
     "pdgn_interp_fwd": (_I, [_P, _P, _P, _I, _I, _I, _I, _P, _P]),
     "pdgn_interp_bwd": (_I, [_P, _P, _P, _I, _I, _I, _I, _P, _P]),
     "pdgn_chamfer_min": (_I, [_P, _P, _I, _I, _I, _I, _P, _P, _P, _P, _P]),

@@ -71,6 +71,132 @@ __global__ void __launch_bounds__(GT) group_bwd_kernel(const float* __restrict__
     }
 }
 
+// ---------------------------------------------------------------- grouping, shared-memory staged (C >= 8)
+// The random 4-byte gathers of the kernels above are served by L1 at ~10+ cycles per warp load; for feature-sized C that,
+// not HBM, is the limit (3.3 TB/s = 51 % of the measured copy peak at B=35, C=256, n=m=1024, k=10).  Staging the CC
+// feature rows of one (batch, channel chunk) in shared memory turns them into 32-bank gathers, leaving the streaming of
+// the [B,C,m,k] tensor as the only HBM traffic.
+constexpr int GS_ROW_BYTES = 64 * 1024;   // shared budget for staged rows per CTA (3 CTAs / SM)
+
+__global__ void __launch_bounds__(GT) group_fwd_smem_kernel(const float* __restrict__ points, const int* __restrict__ idx, int c,
+                                                           int n, int mk, int cc_max, int jpart, float* __restrict__ out) {
+    extern __shared__ __align__(16) float rows[];  // [cc][n]
+    const int bz = blockIdx.z;
+    const int c0 = blockIdx.y * cc_max, cc = min(cc_max, c - c0);
+    const float* src = points + ((size_t)bz * c + c0) * n;  // cc consecutive rows are one contiguous block
+    for (int e = threadIdx.x; e < cc * n; e += GT) rows[e] = __ldg(src + e);
+    __syncthreads();
+    const long long e_end = min((long long)mk, (long long)(blockIdx.x + 1) * jpart);
+    const int* ip = idx + (size_t)bz * mk;
+    float* dst0 = out + ((size_t)bz * c + c0) * mk;
+    for (long long e = (long long)blockIdx.x * jpart + threadIdx.x * 4; e < e_end; e += GT * 4) {
+        const int4 id = *reinterpret_cast<const int4*>(ip + e);
+        const float* r = rows;
+        float* dst = dst0 + e;
+#pragma unroll 4
+        for (int ch = 0; ch < cc; ++ch, r += n, dst += mk) st_stream4(dst, make_float4(r[id.x], r[id.y], r[id.z], r[id.w]));
+    }
+}
+
+// Inverse index of idx[b] (values in [0,n), mk entries): offs[b][n+1], pos[b][mk] with every list sorted ascending, so
+// the pull kernel below adds each target's contributions in a fixed order (deterministic, unlike float atomics).
+template <typename IdxT>
+__global__ void __launch_bounds__(1024) csr_build_kernel(const IdxT* __restrict__ idx, int n, int mk, int* __restrict__ offs,
+                                                        int* __restrict__ pos) {
+    extern __shared__ int csr_sm[];  // cnt[n] | cursor[n] | warp sums[32]
+    int* cnt = csr_sm;
+    int* cursor = csr_sm + n;
+    int* wsum = cursor + n;
+    const int bz = blockIdx.x, t = threadIdx.x, T = blockDim.x;
+    const IdxT* ip = idx + (size_t)bz * mk;
+    int* ob = offs + (size_t)bz * (n + 1);
+    int* pb = pos + (size_t)bz * mk;
+    for (int p = t; p < n; p += T) cnt[p] = 0;
+    __syncthreads();
+    for (int e = t; e < mk; e += T) atomicAdd(&cnt[(int)ip[e]], 1);
+    __syncthreads();
+    // exclusive scan: each thread owns a contiguous slice of targets
+    const int per = (n + T - 1) / T;
+    const int lo = min(n, t * per), hi = min(n, lo + per);
+    int local = 0;
+    for (int p = lo; p < hi; ++p) local += cnt[p];
+    int incl = local;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        const int v = __shfl_up_sync(kFull, incl, o);
+        if ((t & 31) >= o) incl += v;
+    }
+    if ((t & 31) == 31) wsum[t >> 5] = incl;
+    __syncthreads();
+    if (t < 32) {
+        int v = (t < (T >> 5)) ? wsum[t] : 0;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            const int u = __shfl_up_sync(kFull, v, o);
+            if (t >= o) v += u;
+        }
+        wsum[t] = v;  // inclusive over warps
+    }
+    __syncthreads();
+    int run = incl - local + ((t >> 5) ? wsum[(t >> 5) - 1] : 0);
+    for (int p = lo; p < hi; ++p) {
+        cursor[p] = run;
+        ob[p] = run;
+        run += cnt[p];
+    }
+    if (t == T - 1) ob[n] = mk;
+    __syncthreads();
+    for (int e = t; e < mk; e += T) pb[atomicAdd(&cursor[(int)ip[e]], 1)] = e;
+    __syncthreads();
+    for (int p = t; p < n; p += T) {  // insertion sort of each (short) list
+        const int a = cursor[p] - cnt[p], b = cursor[p];
+        for (int i = a + 1; i < b; ++i) {
+            const int v = pb[i];
+            int j = i - 1;
+            while (j >= a && pb[j] > v) {
+                pb[j + 1] = pb[j];
+                --j;
+            }
+            pb[j + 1] = v;
+        }
+    }
+}
+
+// grad_points[b,ch,p] += sum over the positions e with idx[b,e] == p of grad_out[b,ch,e]: the cc rows of one (batch,
+// channel chunk) are streamed once into shared memory, every thread pulls the lists of its targets from there.
+__global__ void __launch_bounds__(512) group_bwd_pull_kernel(const float* __restrict__ grad_out, const int* __restrict__ offs,
+                                                            const int* __restrict__ pos, int c, int n, int mk, int cc_max,
+                                                            float* __restrict__ grad_points) {
+    extern __shared__ __align__(16) float rows[];  // [cc][mk]
+    const int bz = blockIdx.y;
+    const int c0 = blockIdx.x * cc_max, cc = min(cc_max, c - c0);
+    const float* src = grad_out + ((size_t)bz * c + c0) * mk;
+    if ((mk & 3) == 0) {
+        const float4* s4 = reinterpret_cast<const float4*>(src);
+        float4* r4 = reinterpret_cast<float4*>(rows);
+        for (int e = threadIdx.x; e < cc * (mk >> 2); e += blockDim.x) r4[e] = __ldcs(s4 + e);
+    } else {
+        for (int e = threadIdx.x; e < cc * mk; e += blockDim.x) rows[e] = __ldcs(src + e);
+    }
+    __syncthreads();
+    const int* ob = offs + (size_t)bz * (n + 1);
+    const int* pb = pos + (size_t)bz * mk;
+    float* dst = grad_points + ((size_t)bz * c + c0) * n;
+    for (int p = threadIdx.x; p < n; p += blockDim.x) {
+        const int a = ob[p], b = ob[p + 1];
+        float acc[4] = {0.f, 0.f, 0.f, 0.f};
+        for (int q = a; q < b; ++q) {
+            const int e = __ldg(pb + q);
+#pragma unroll
+            for (int ch = 0; ch < 4; ++ch)
+                if (ch < cc) acc[ch] += rows[ch * mk + e];
+        }
+#pragma unroll
+        for (int ch = 0; ch < 4; ++ch)
+            if (ch < cc) dst[(size_t)ch * n + p] += acc[ch];
+    }
+}
+
 // ---------------------------------------------------------------- interpolation forward
 // out[b,ch,j] = fma(w2,p[i2], fma(w0,p[i0], w1*p[i1]))  -- the compiled order of
 // weight[0]*points[idx[0]] + weight[1]*points[idx[1]] + weight[2]*points[idx[2]] (interpolation_cuda_kernel.cu:194).
@@ -201,6 +327,118 @@ __global__ void __launch_bounds__(GT) edge_bwd_kernel(const float* __restrict__ 
     }
 }
 
+// ---------------------------------------------------------------- interpolation / edge features, shared-memory staged
+// Same two ideas as the staged grouping kernels: gathers out of shared rows, backward as a deterministic pull
+// through the inverse index (csr_build_kernel) instead of float atomics.
+
+// out[b,ch,j] for 4 consecutive j per thread; rows = cc feature rows of m floats.
+__global__ void __launch_bounds__(GT) interp_fwd_smem_kernel(const float* __restrict__ points, const int* __restrict__ idx,
+                                                            const float* __restrict__ weight, int c, int m, int n, int cc_max,
+                                                            int jpart, float* __restrict__ out) {
+    extern __shared__ __align__(16) float rows[];  // [cc][m]
+    const int bz = blockIdx.z;
+    const int c0 = blockIdx.y * cc_max, cc = min(cc_max, c - c0);
+    const float* src = points + ((size_t)bz * c + c0) * m;
+    for (int e = threadIdx.x; e < cc * m; e += GT) rows[e] = __ldg(src + e);
+    __syncthreads();
+    const int j_end = min(n, (int)(blockIdx.x + 1) * jpart);
+    float* dst0 = out + ((size_t)bz * c + c0) * n;
+    for (int j = blockIdx.x * jpart + threadIdx.x * 4; j < j_end; j += GT * 4) {
+        const int* ip = idx + ((size_t)bz * n + j) * 3;
+        const float* wp = weight + ((size_t)bz * n + j) * 3;
+        int id[12];
+        float w[12];
+#pragma unroll
+        for (int q = 0; q < 3; ++q) {
+            const int4 a = reinterpret_cast<const int4*>(ip)[q];
+            const float4 f = reinterpret_cast<const float4*>(wp)[q];
+            id[4 * q] = a.x; id[4 * q + 1] = a.y; id[4 * q + 2] = a.z; id[4 * q + 3] = a.w;
+            w[4 * q] = f.x; w[4 * q + 1] = f.y; w[4 * q + 2] = f.z; w[4 * q + 3] = f.w;
+        }
+        const float* r = rows;
+        float* dst = dst0 + j;
+#pragma unroll 2
+        for (int ch = 0; ch < cc; ++ch, r += m, dst += n) {
+            float4 o;
+            o.x = __fmaf_rn(w[2], r[id[2]], __fmaf_rn(w[0], r[id[0]], __fmul_rn(w[1], r[id[1]])));
+            o.y = __fmaf_rn(w[5], r[id[5]], __fmaf_rn(w[3], r[id[3]], __fmul_rn(w[4], r[id[4]])));
+            o.z = __fmaf_rn(w[8], r[id[8]], __fmaf_rn(w[6], r[id[6]], __fmul_rn(w[7], r[id[7]])));
+            o.w = __fmaf_rn(w[11], r[id[11]], __fmaf_rn(w[9], r[id[9]], __fmul_rn(w[10], r[id[10]])));
+            st_stream4(dst, o);
+        }
+    }
+}
+
+// grad_points[b,ch,p] += sum over entries e = 3*j+t with idx[b,e] == p of fmul(grad_out[b,ch,j], weight[b,e])
+// (each product rounded like the reference's atomicAdd operand; added in ascending e: deterministic).
+__global__ void __launch_bounds__(512) interp_bwd_pull_kernel(const float* __restrict__ grad_out, const float* __restrict__ weight,
+                                                             const int* __restrict__ offs, const int* __restrict__ pos, int c, int n,
+                                                             int m, int cc_max, float* __restrict__ grad_points) {
+    extern __shared__ __align__(16) float rows[];  // [cc][n] grad_out rows, then [3n] weights
+    const int bz = blockIdx.y;
+    const int c0 = blockIdx.x * cc_max, cc = min(cc_max, c - c0);
+    const float* src = grad_out + ((size_t)bz * c + c0) * n;
+    for (int e = threadIdx.x; e < cc * n; e += blockDim.x) rows[e] = __ldcs(src + e);
+    float* wsm = rows + (size_t)cc_max * n;
+    const float* wsrc = weight + (size_t)bz * n * 3;
+    for (int e = threadIdx.x; e < 3 * n; e += blockDim.x) wsm[e] = __ldg(wsrc + e);
+    __syncthreads();
+    const int* ob = offs + (size_t)bz * (m + 1);
+    const int* pb = pos + (size_t)bz * 3 * n;
+    float* dst = grad_points + ((size_t)bz * c + c0) * m;
+    for (int p = threadIdx.x; p < m; p += blockDim.x) {
+        const int a = ob[p], b = ob[p + 1];
+        float acc[8];
+#pragma unroll
+        for (int ch = 0; ch < 8; ++ch) acc[ch] = 0.f;
+        for (int q = a; q < b; ++q) {
+            const int e = __ldg(pb + q);
+            const int j = e / 3;
+            const float w = wsm[e];
+#pragma unroll
+            for (int ch = 0; ch < 8; ++ch)
+                if (ch < cc) acc[ch] += __fmul_rn(rows[ch * n + j], w);
+        }
+#pragma unroll
+        for (int ch = 0; ch < 8; ++ch)
+            if (ch < cc) dst[(size_t)ch * m + p] += acc[ch];
+    }
+}
+
+// edge features backward as a pull: grad_x[b,ch,i] += sum_s (g0[i,s] - g1[i,s]) + sum over entries e with idx[b,e] == i of g1[e]
+// (g0 = grad_ee[b,ch], g1 = grad_ee[b,c+ch], both [n*k]); the g1 row is staged in shared memory.
+__global__ void __launch_bounds__(512) edge_bwd_pull_kernel(const float* __restrict__ grad_ee, const int* __restrict__ offs,
+                                                           const int* __restrict__ pos, int c, int n, int k, int cc_max,
+                                                           float* __restrict__ grad_x) {
+    extern __shared__ __align__(16) float rows[];  // [cc][2][n*k]: g0 | g1 per channel
+    const int bz = blockIdx.y;
+    const int c0 = blockIdx.x * cc_max, cc = min(cc_max, c - c0);
+    const int nk = n * k;
+    for (int ch = 0; ch < cc; ++ch) {
+        const float* s0 = grad_ee + ((size_t)bz * 2 * c + c0 + ch) * nk;
+        const float* s1 = grad_ee + ((size_t)bz * 2 * c + c + c0 + ch) * nk;
+        float* r0 = rows + (size_t)ch * 2 * nk;
+        for (int e = threadIdx.x; e < nk; e += blockDim.x) {
+            r0[e] = __ldcs(s0 + e);
+            r0[nk + e] = __ldcs(s1 + e);
+        }
+    }
+    __syncthreads();
+    const int* ob = offs + (size_t)bz * (n + 1);
+    const int* pb = pos + (size_t)bz * nk;
+    for (int i = threadIdx.x; i < n; i += blockDim.x) {
+        const int a = ob[i], b = ob[i + 1];
+        for (int ch = 0; ch < cc; ++ch) {
+            const float* r0 = rows + (size_t)ch * 2 * nk;
+            const float* r1 = r0 + nk;
+            float acc = 0.f;
+            for (int s = 0; s < k; ++s) acc += r0[i * k + s] - r1[i * k + s];
+            for (int q = a; q < b; ++q) acc += r1[__ldg(pb + q)];
+            grad_x[((size_t)bz * c + c0 + ch) * n + i] += acc;
+        }
+    }
+}
+
 // channels per CTA: keep >= ~4 waves of CTAs while amortising the index read over as many channels as possible
 static int pick_cpb(long long ctas_per_channel_group, int c) {
     int cpb = c;
@@ -221,6 +459,26 @@ extern "C" int pdgn_group_fwd(const float* points, const int* idx, int b, int c,
     if (b == 0 || c == 0 || mk == 0) return PDGN_OK;
     if (mk > 0x7fffffffLL || b > 65535) return PDGN_ERR_UNSUPPORTED;
     const bool vec = (mk % 4 == 0) && ((reinterpret_cast<uintptr_t>(out) | reinterpret_cast<uintptr_t>(idx)) % 16 == 0);
+    if (vec && c >= 8 && (size_t)n * 4 * 4 <= GS_ROW_BYTES) {
+        // shared-memory staged path: cc rows of n floats per CTA, position range split so that >= ~4 waves of CTAs exist
+        int cc = 4;
+        while (cc * 2 <= c && (size_t)cc * 2 * n * 4 <= GS_ROW_BYTES) cc *= 2;
+        const int chunks = (c + cc - 1) / cc;
+        long long parts = (4LL * 148 * 3 + (long long)chunks * b - 1) / ((long long)chunks * b);
+        const long long max_parts = (mk + GT * 4 - 1) / (GT * 4);
+        if (parts > max_parts) parts = max_parts;
+        if (parts < 1) parts = 1;
+        long long jpart = (mk + parts - 1) / parts;
+        jpart = (jpart + GT * 4 - 1) / (GT * 4) * (GT * 4);
+        parts = (mk + jpart - 1) / jpart;
+        const size_t smem = (size_t)cc * n * 4;
+        PDGN_CUDA(cudaFuncSetAttribute(group_fwd_smem_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        dim3 grid((unsigned)parts, chunks, b);
+        if (grid.y > 65535) return PDGN_ERR_UNSUPPORTED;
+        group_fwd_smem_kernel<<<grid, GT, smem, (cudaStream_t)stream>>>(points, idx, c, n, (int)mk, cc, (int)jpart, out);
+        PDGN_CHECK_LAUNCH();
+        return PDGN_OK;
+    }
     const long long per = vec ? 4 : 1;
     const unsigned gx = (unsigned)((mk + GT * per - 1) / (GT * per));
     const int cpb = pick_cpb((long long)gx * b, c);
@@ -228,6 +486,40 @@ extern "C" int pdgn_group_fwd(const float* points, const int* idx, int b, int c,
     if (grid.y > 65535) return PDGN_ERR_UNSUPPORTED;
     if (vec) group_fwd_kernel<true><<<grid, GT, 0, (cudaStream_t)stream>>>(points, idx, c, n, (int)mk, cpb, out);
     else group_fwd_kernel<false><<<grid, GT, 0, (cudaStream_t)stream>>>(points, idx, c, n, (int)mk, cpb, out);
+    PDGN_CHECK_LAUNCH();
+    return PDGN_OK;
+}
+
+// Workspace form of the backward: deterministic pull through an inverse index built in `workspace`
+// (pdgn_group_bwd_workspace bytes).  Falls back to the atomic kernel when the rows do not fit shared memory.
+extern "C" size_t pdgn_group_bwd_workspace(int b, int n, int m, int k) {
+    if (b < 0 || n < 0 || m < 0 || k < 0) return 0;
+    return ((size_t)b * ((size_t)n + 1) + (size_t)b * m * k) * sizeof(int) + 256;
+}
+
+extern "C" int pdgn_group_bwd_ws(const float* grad_out, const int* idx, int b, int c, int n, int m, int k, float* grad_points,
+                                 void* workspace, size_t workspace_bytes, void* stream) {
+    PDGN_GATHER_ARGS_OK(grad_out && idx && grad_points && b >= 0 && c >= 0 && n > 0 && m >= 0 && k >= 0);
+    const long long mk = (long long)m * k;
+    if (b == 0 || c == 0 || mk == 0) return PDGN_OK;
+    if (mk > 0x7fffffffLL || b > 65535) return PDGN_ERR_UNSUPPORTED;
+    const size_t row_bytes = (size_t)mk * 4;
+    const size_t csr_smem = ((size_t)2 * n + 32) * sizeof(int);
+    if (!workspace || c < 4 || row_bytes > 200 * 1024 || csr_smem > 200 * 1024)
+        return pdgn_group_bwd(grad_out, idx, b, c, n, m, k, grad_points, stream);
+    if (workspace_bytes < pdgn_group_bwd_workspace(b, n, m, k) - 256 || (reinterpret_cast<uintptr_t>(workspace) & 3)) return PDGN_ERR_WORKSPACE;
+    cudaStream_t st = (cudaStream_t)stream;
+    int* offs = reinterpret_cast<int*>(workspace);
+    int* pos = offs + (size_t)b * (n + 1);
+    PDGN_CUDA(cudaFuncSetAttribute(csr_build_kernel<int>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)csr_smem));
+    csr_build_kernel<int><<<b, 1024, csr_smem, st>>>(idx, n, (int)mk, offs, pos);
+    PDGN_CHECK_LAUNCH();
+    int cc = 1;
+    while (cc < 4 && (size_t)cc * 2 * row_bytes <= 100 * 1024) cc *= 2;
+    const size_t smem = (size_t)cc * row_bytes;
+    PDGN_CUDA(cudaFuncSetAttribute(group_bwd_pull_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    dim3 grid((c + cc - 1) / cc, b);
+    group_bwd_pull_kernel<<<grid, 512, smem, st>>>(grad_out, offs, pos, c, n, (int)mk, cc, grad_points);
     PDGN_CHECK_LAUNCH();
     return PDGN_OK;
 }

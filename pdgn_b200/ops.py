@@ -64,8 +64,12 @@ def group_bwd(grad_out, idx, n):
     _req(grad_out, "grad_out"); _req(idx, "idx", torch.int32)
     b, c, m, k = grad_out.shape
     grad = torch.zeros((b, c, n), dtype=torch.float32, device=grad_out.device)
+    L = lib()
+    ws_bytes = L.pdgn_group_bwd_workspace(b, n, m, k)
+    ws = torch.empty((ws_bytes,), dtype=torch.uint8, device=grad_out.device)
     with torch.cuda.device(grad_out.device):
-        check(lib().pdgn_group_bwd(grad_out.data_ptr(), idx.data_ptr(), b, c, n, m, k, grad.data_ptr(), _stream(grad_out)), "pdgn_group_bwd")
+        check(L.pdgn_group_bwd_ws(grad_out.data_ptr(), idx.data_ptr(), b, c, n, m, k, grad.data_ptr(), ws.data_ptr(), ws_bytes,
+                                  _stream(grad_out)), "pdgn_group_bwd_ws")
     return grad
 
 
