@@ -359,6 +359,21 @@ def bench_gathers(dev, hbm_gbs, src):
         res[tag] = {"fwd_ms": f_ms, "fwd_gbs": bytes_fwd / (f_ms * 1e-3) / 1e9, "fwd_frac": bytes_fwd / (f_ms * 1e-3) / 1e9 / hbm_gbs,
                     "bwd_ms": b_ms, "bwd_gbs": bytes_fwd / (b_ms * 1e-3) / 1e9, "bwd_frac": bytes_fwd / (b_ms * 1e-3) / 1e9 / hbm_gbs,
                     "algorithmic_mb": bytes_fwd / 1e6}
+    # three-point interpolation, 1024 -> 2048 points, C=256; bytes = 4(BCn + BCm) + 24 Bn
+    b, c, m, n = 35, 256, 1024, 2048
+    feat = torch.from_numpy(rng.standard_normal((b, c, m)).astype(np.float32)).to(dev)
+    idx3 = torch.from_numpy(rng.integers(0, m, (b, n, 3)).astype(np.int32)).to(dev)
+    w3 = torch.rand((b, n, 3), device=dev)
+    out = torch.empty((b, c, n), dtype=torch.float32, device=dev)
+    grad = torch.zeros((b, c, m), dtype=torch.float32, device=dev)
+    ws_bytes = L.pdgn_interp_bwd_workspace(b, n, m)
+    ws = torch.empty((ws_bytes,), dtype=torch.uint8, device=dev)
+    f_ms = _time_ms(lambda: L.pdgn_interp_fwd(feat.data_ptr(), idx3.data_ptr(), w3.data_ptr(), b, c, m, n, out.data_ptr(), st), 10, flush)
+    b_ms = _time_ms(lambda: L.pdgn_interp_bwd_ws(out.data_ptr(), idx3.data_ptr(), w3.data_ptr(), b, c, n, m, grad.data_ptr(), ws.data_ptr(), ws_bytes, st), 10, flush)
+    nbytes = 4.0 * (b * c * n + b * c * m) + 24.0 * b * n
+    res["interp_c256"] = {"fwd_ms": f_ms, "fwd_gbs": nbytes / (f_ms * 1e-3) / 1e9, "fwd_frac": nbytes / (f_ms * 1e-3) / 1e9 / hbm_gbs,
+                          "bwd_ms": b_ms, "bwd_gbs": nbytes / (b_ms * 1e-3) / 1e9, "bwd_frac": nbytes / (b_ms * 1e-3) / 1e9 / hbm_gbs,
+                          "algorithmic_mb": nbytes / 1e6}
     return res
 
 

@@ -75,6 +75,10 @@ int pdgn_interp_fwd(const float *points, const int *idx, const float *weight, in
                     void *stream);
 int pdgn_interp_bwd(const float *grad_out, const int *idx, const float *weight, int b, int c, int n, int m,
                     float *grad_points, void *stream);
+/* Deterministic pull form of the backward (see pdgn_group_bwd_ws); workspace = pdgn_interp_bwd_workspace(b,n,m) bytes. */
+size_t pdgn_interp_bwd_workspace(int b, int n, int m);
+int pdgn_interp_bwd_ws(const float *grad_out, const int *idx, const float *weight, int b, int c, int n, int m,
+                       float *grad_points, void *workspace, size_t workspace_bytes, void *stream);
 
 /* ---- directional nearest-neighbour distance (Chamfer building block) --------------------------------
  * Replaces nndistance(b,n,xyz,m,xyz2,result,result_i,result2,result2_i,stream)
@@ -122,6 +126,10 @@ int pdgn_knn_feat(const float *x, int b, int c, int n, int k, int skip, int64_t 
 int pdgn_edge_feat_fwd(const float *x, const int64_t *idx, int b, int c, int n, int k, float *ee, void *stream);
 int pdgn_edge_feat_bwd(const float *grad_ee, const int64_t *idx, int b, int c, int n, int k, float *grad_x,
                        void *stream);
+/* Deterministic pull form (see pdgn_group_bwd_ws); workspace = pdgn_edge_feat_bwd_workspace(b,n,k) bytes. */
+size_t pdgn_edge_feat_bwd_workspace(int b, int n, int k);
+int pdgn_edge_feat_bwd_ws(const float *grad_ee, const int64_t *idx, int b, int c, int n, int k, float *grad_x,
+                          void *workspace, size_t workspace_bytes, void *stream);
 
 #ifdef __cplusplus
 }

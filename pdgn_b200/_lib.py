@@ -27,6 +27,8 @@ SIGNATURES = {
     "pdgn_group_bwd_ws": (_I, [_P, _P, _I, _I, _I, _I, _I, _P, _P, _SZ, _P]),
     "pdgn_interp_fwd": (_I, [_P, _P, _P, _I, _I, _I, _I, _P, _P]),
     "pdgn_interp_bwd": (_I, [_P, _P, _P, _I, _I, _I, _I, _P, _P]),
+    "pdgn_interp_bwd_workspace": (_SZ, [_I, _I, _I]),
+    "pdgn_interp_bwd_ws": (_I, [_P, _P, _P, _I, _I, _I, _I, _P, _P, _SZ, _P]),
     "pdgn_chamfer_min": (_I, [_P, _P, _I, _I, _I, _I, _P, _P, _P, _P, _P]),
     "pdgn_chamfer_bwd": (_I, [_P, _P, _I, _I, _I, _I, _P, _P, _P, _P, _P, _P, _P]),
     "pdgn_cd_allpairs_workspace": (_SZ, [_I, _I, _I]),
@@ -35,6 +37,8 @@ SIGNATURES = {
     "pdgn_knn_feat": (_I, [_P, _I, _I, _I, _I, _I, _P, _P, _P]),
     "pdgn_edge_feat_fwd": (_I, [_P, _P, _I, _I, _I, _I, _P, _P]),
     "pdgn_edge_feat_bwd": (_I, [_P, _P, _I, _I, _I, _I, _P, _P]),
+    "pdgn_edge_feat_bwd_workspace": (_SZ, [_I, _I, _I]),
+    "pdgn_edge_feat_bwd_ws": (_I, [_P, _P, _I, _I, _I, _I, _P, _P, _SZ, _P]),
 }
 
 

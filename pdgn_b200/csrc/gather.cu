@@ -84,7 +84,11 @@ __global__ void __launch_bounds__(GT) group_fwd_smem_kernel(const float* __restr
     const int bz = blockIdx.z;
     const int c0 = blockIdx.y * cc_max, cc = min(cc_max, c - c0);
     const float* src = points + ((size_t)bz * c + c0) * n;  // cc consecutive rows are one contiguous block
-    for (int e = threadIdx.x; e < cc * n; e += GT) rows[e] = __ldg(src + e);
+    if (((cc * n) & 3) == 0 && (reinterpret_cast<uintptr_t>(src) & 15) == 0) {
+        for (int e = threadIdx.x; e < (cc * n) >> 2; e += GT) reinterpret_cast<float4*>(rows)[e] = __ldg(reinterpret_cast<const float4*>(src) + e);
+    } else {
+        for (int e = threadIdx.x; e < cc * n; e += GT) rows[e] = __ldg(src + e);
+    }
     __syncthreads();
     const long long e_end = min((long long)mk, (long long)(blockIdx.x + 1) * jpart);
     const int* ip = idx + (size_t)bz * mk;
@@ -98,25 +102,31 @@ __global__ void __launch_bounds__(GT) group_fwd_smem_kernel(const float* __restr
     }
 }
 
-// Inverse index of idx[b] (values in [0,n), mk entries): offs[b][n+1], pos[b][mk] with every list sorted ascending, so
-// the pull kernel below adds each target's contributions in a fixed order (deterministic, unlike float atomics).
+// Inverse index of idx[b] (values in [0,n), mk entries): offs[b][n+1], pos[b][mk] with every list in ascending
+// position order, so the pull kernels add each target's contributions in a fixed order (deterministic, unlike the
+// reference's float atomics).  The fill is a STABLE counting sort without atomics on the order: entries are taken in
+// tiles of blockDim.x consecutive positions; inside a warp __match_any_sync ranks equal targets by lane, and the warps
+// of a tile take their turn in order (one barrier per warp), so equal targets keep their position order regardless of
+// how skewed the index distribution is (feature-space kNN graphs have hubs with thousands of incoming edges).
+constexpr int CSR_T = 1024;
+
 template <typename IdxT>
-__global__ void __launch_bounds__(1024) csr_build_kernel(const IdxT* __restrict__ idx, int n, int mk, int* __restrict__ offs,
-                                                        int* __restrict__ pos) {
+__global__ void __launch_bounds__(CSR_T) csr_build_kernel(const IdxT* __restrict__ idx, int n, int mk, int* __restrict__ offs,
+                                                         int* __restrict__ pos) {
     extern __shared__ int csr_sm[];  // cnt[n] | cursor[n] | warp sums[32]
     int* cnt = csr_sm;
     int* cursor = csr_sm + n;
     int* wsum = cursor + n;
-    const int bz = blockIdx.x, t = threadIdx.x, T = blockDim.x;
+    const int bz = blockIdx.x, t = threadIdx.x, lane = t & 31, warp = t >> 5;
     const IdxT* ip = idx + (size_t)bz * mk;
     int* ob = offs + (size_t)bz * (n + 1);
     int* pb = pos + (size_t)bz * mk;
-    for (int p = t; p < n; p += T) cnt[p] = 0;
+    for (int p = t; p < n; p += CSR_T) cnt[p] = 0;
     __syncthreads();
-    for (int e = t; e < mk; e += T) atomicAdd(&cnt[(int)ip[e]], 1);
+    for (int e = t; e < mk; e += CSR_T) atomicAdd(&cnt[(int)ip[e]], 1);  // integer counts: order irrelevant
     __syncthreads();
     // exclusive scan: each thread owns a contiguous slice of targets
-    const int per = (n + T - 1) / T;
+    const int per = (n + CSR_T - 1) / CSR_T;
     const int lo = min(n, t * per), hi = min(n, lo + per);
     int local = 0;
     for (int p = lo; p < hi; ++p) local += cnt[p];
@@ -124,12 +134,12 @@ __global__ void __launch_bounds__(1024) csr_build_kernel(const IdxT* __restrict_
 #pragma unroll
     for (int o = 1; o < 32; o <<= 1) {
         const int v = __shfl_up_sync(kFull, incl, o);
-        if ((t & 31) >= o) incl += v;
+        if (lane >= o) incl += v;
     }
-    if ((t & 31) == 31) wsum[t >> 5] = incl;
+    if (lane == 31) wsum[warp] = incl;
     __syncthreads();
     if (t < 32) {
-        int v = (t < (T >> 5)) ? wsum[t] : 0;
+        int v = wsum[t];
 #pragma unroll
         for (int o = 1; o < 32; o <<= 1) {
             const int u = __shfl_up_sync(kFull, v, o);
@@ -138,39 +148,125 @@ __global__ void __launch_bounds__(1024) csr_build_kernel(const IdxT* __restrict_
         wsum[t] = v;  // inclusive over warps
     }
     __syncthreads();
-    int run = incl - local + ((t >> 5) ? wsum[(t >> 5) - 1] : 0);
+    int run = incl - local + (warp ? wsum[warp - 1] : 0);
     for (int p = lo; p < hi; ++p) {
         cursor[p] = run;
         ob[p] = run;
         run += cnt[p];
     }
-    if (t == T - 1) ob[n] = mk;
+    if (t == CSR_T - 1) ob[n] = mk;
     __syncthreads();
-    for (int e = t; e < mk; e += T) pb[atomicAdd(&cursor[(int)ip[e]], 1)] = e;
-    __syncthreads();
-    for (int p = t; p < n; p += T) {  // insertion sort of each (short) list
-        const int a = cursor[p] - cnt[p], b = cursor[p];
-        for (int i = a + 1; i < b; ++i) {
-            const int v = pb[i];
-            int j = i - 1;
-            while (j >= a && pb[j] > v) {
-                pb[j + 1] = pb[j];
-                --j;
+    const unsigned lt = (1u << lane) - 1u;
+    for (int e0 = 0; e0 < mk; e0 += CSR_T) {
+        const int e = e0 + t;
+        const bool valid = e < mk;
+        const int tgt = valid ? (int)ip[e] : -1 - lane;               // invalid lanes match nobody
+        const unsigned peers = __match_any_sync(kFull, tgt);
+        const int rank = __popc(peers & lt);
+        int base = 0;
+        for (int w = 0; w < CSR_T / 32; ++w) {
+            if (warp == w && valid && rank == 0) {                    // one leader per distinct target in this warp
+                base = cursor[tgt];
+                cursor[tgt] = base + __popc(peers);
             }
-            pb[j + 1] = v;
+            __syncthreads();
+        }
+        base = __shfl_sync(kFull, base, __ffs(peers) - 1);
+        if (valid) pb[base + rank] = e;
+    }
+}
+
+// Multi-channel pull: acc[ch] += value(ch, e) for the entries pb[a..b) in list order (index loads four at a time,
+// every entry feeds all CC channel accumulators, so the list is read once per channel chunk).
+template <int CC, class F>
+__device__ __forceinline__ void pull_list(const int* __restrict__ pb, int a, int b, float (&acc)[CC], F value) {
+    int q = a;
+    for (; q + 4 <= b; q += 4) {
+        const int e0 = __ldg(pb + q), e1 = __ldg(pb + q + 1), e2 = __ldg(pb + q + 2), e3 = __ldg(pb + q + 3);
+#pragma unroll
+        for (int ch = 0; ch < CC; ++ch) {
+            acc[ch] += value(ch, e0);
+            acc[ch] += value(ch, e1);
+            acc[ch] += value(ch, e2);
+            acc[ch] += value(ch, e3);
+        }
+    }
+    for (; q < b; ++q) {
+        const int e = __ldg(pb + q);
+#pragma unroll
+        for (int ch = 0; ch < CC; ++ch) acc[ch] += value(ch, e);
+    }
+}
+
+constexpr int PULL_LONG = 64;  // lists longer than this are summed by a whole warp
+constexpr int PULL_CC = 4;     // channel rows staged per CTA (upper bound)
+
+// Long list: lane l sums entries a+l, a+l+32, ... in order, then a fixed butterfly combines the 32 partial sums.
+template <int CC, class F>
+__device__ __forceinline__ void pull_list_warp(const int* __restrict__ pb, int a, int b, int lane, float (&acc)[CC], F value) {
+    for (int q = a + lane; q < b; q += 32) {
+        const int e = __ldg(pb + q);
+#pragma unroll
+        for (int ch = 0; ch < CC; ++ch) acc[ch] += value(ch, e);
+    }
+#pragma unroll
+    for (int ch = 0; ch < CC; ++ch)
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) acc[ch] += __shfl_xor_sync(kFull, acc[ch], o);
+}
+
+// Shared skeleton of the three pull kernels.  `value(ch, e)` = contribution of entry e to channel ch (ch < cc is the
+// caller's business: rows beyond cc are zero-filled), `extra(ch, p)` = per-target term added first, `out(ch, p)` = address.
+// Every (channel, target) is written by exactly one thread with one RED.ADD onto the caller's buffer => deterministic.
+template <class V, class X, class O>
+__device__ __forceinline__ void pull_targets(const int* __restrict__ ob, const int* __restrict__ pb, int ntargets, int cc,
+                                             int* nlong, int* longlist, V value, X extra, O out) {
+    for (int p = threadIdx.x; p < ntargets; p += blockDim.x) {
+        const int a = ob[p], b = ob[p + 1];
+        float acc[PULL_CC];
+#pragma unroll
+        for (int ch = 0; ch < PULL_CC; ++ch) acc[ch] = ch < cc ? extra(ch, p) : 0.f;
+        bool deferred = false;
+        if (b - a > PULL_LONG) {
+            const int slot = atomicAdd(nlong, 1);
+            if (slot < 512) {
+                longlist[slot] = p;
+                deferred = true;
+            }
+        }
+        if (!deferred) pull_list<PULL_CC>(pb, a, b, acc, value);
+#pragma unroll
+        for (int ch = 0; ch < PULL_CC; ++ch)
+            if (ch < cc) atomicAdd(out(ch, p), acc[ch]);
+    }
+    __syncthreads();
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nw = blockDim.x >> 5;
+    const int nl = min(*nlong, 512);
+    for (int i = warp; i < nl; i += nw) {
+        const int p = longlist[i];
+        float acc[PULL_CC];
+#pragma unroll
+        for (int ch = 0; ch < PULL_CC; ++ch) acc[ch] = 0.f;
+        pull_list_warp<PULL_CC>(pb, ob[p], ob[p + 1], lane, acc, value);
+        if (lane == 0) {
+#pragma unroll
+            for (int ch = 0; ch < PULL_CC; ++ch)
+                if (ch < cc) atomicAdd(out(ch, p), acc[ch]);
         }
     }
 }
 
-// grad_points[b,ch,p] += sum over the positions e with idx[b,e] == p of grad_out[b,ch,e]: the cc rows of one (batch,
+// grad_points[b,ch,p] += sum over the positions e with idx[b,e] == p of grad_out[b,ch,e]: the rows of one (batch,
 // channel chunk) are streamed once into shared memory, every thread pulls the lists of its targets from there.
 __global__ void __launch_bounds__(512) group_bwd_pull_kernel(const float* __restrict__ grad_out, const int* __restrict__ offs,
                                                             const int* __restrict__ pos, int c, int n, int mk, int cc_max,
                                                             float* __restrict__ grad_points) {
-    extern __shared__ __align__(16) float rows[];  // [cc][mk]
+    extern __shared__ __align__(16) float rows[];  // [PULL_CC][mk] (rows beyond cc zero-filled)
+    __shared__ int nlong, longlist[512];
     const int bz = blockIdx.y;
     const int c0 = blockIdx.x * cc_max, cc = min(cc_max, c - c0);
     const float* src = grad_out + ((size_t)bz * c + c0) * mk;
+    if (threadIdx.x == 0) nlong = 0;
     if ((mk & 3) == 0) {
         const float4* s4 = reinterpret_cast<const float4*>(src);
         float4* r4 = reinterpret_cast<float4*>(rows);
@@ -178,23 +274,165 @@ __global__ void __launch_bounds__(512) group_bwd_pull_kernel(const float* __rest
     } else {
         for (int e = threadIdx.x; e < cc * mk; e += blockDim.x) rows[e] = __ldcs(src + e);
     }
+    for (int e = cc * mk + threadIdx.x; e < cc_max * mk; e += blockDim.x) rows[e] = 0.f;
     __syncthreads();
-    const int* ob = offs + (size_t)bz * (n + 1);
-    const int* pb = pos + (size_t)bz * mk;
     float* dst = grad_points + ((size_t)bz * c + c0) * n;
-    for (int p = threadIdx.x; p < n; p += blockDim.x) {
-        const int a = ob[p], b = ob[p + 1];
-        float acc[4] = {0.f, 0.f, 0.f, 0.f};
-        for (int q = a; q < b; ++q) {
-            const int e = __ldg(pb + q);
-#pragma unroll
-            for (int ch = 0; ch < 4; ++ch)
-                if (ch < cc) acc[ch] += rows[ch * mk + e];
-        }
-#pragma unroll
-        for (int ch = 0; ch < 4; ++ch)
-            if (ch < cc) dst[(size_t)ch * n + p] += acc[ch];
+    const int cm = cc_max;
+    pull_targets(offs + (size_t)bz * (n + 1), pos + (size_t)bz * mk, n, cc, &nlong, longlist,
+                 [&](int ch, int e) { return ch < cm ? rows[(size_t)ch * mk + e] : 0.f; },
+                 [&](int, int) { return 0.f; },
+                 [&](int ch, int p) { return dst + (size_t)ch * n + p; });
+}
+
+// Streaming pull (grouping and edge-feature backward, the two tensors that are hundreds of MB): one CTA walks several
+// channel chunks of one batch element; the CC rows of a chunk arrive by TMA bulk copy (cp.async.bulk + mbarrier) into
+// one of two shared buffers while the 1024 threads pull the previous chunk, so HBM streams continuously and the
+// latency of the list walk hides under it.  MODE 0: rows = grad_out[b,ch,:].  MODE 1: rows = g1 = grad_ee[b,c+ch,:],
+// plus the central term sum_s (g0 - g1)[i,s] read in place.
+template <int CC, int MODE>
+__global__ void __launch_bounds__(1024, 1) pull_stream_kernel(const float* __restrict__ src, const int* __restrict__ offs,
+                                                          const int* __restrict__ pos, int c, int ntargets, int rowlen, int k,
+                                                          int chunks_per_cta, float* __restrict__ dst) {
+    constexpr int NR = MODE == 1 ? 2 * CC : CC;    // rows staged per chunk (MODE 1: CC g0 rows, then CC g1 rows)
+    constexpr int ECACHE = 16;                     // list entries cached in registers across the chunks
+    extern __shared__ __align__(128) float buf[];  // [2][NR*rowlen]
+    __shared__ uint64_t bars[2];
+    __shared__ int nlong, longlist[512];
+    const int bz = blockIdx.y, tid = threadIdx.x;
+    const int nchunks = (c + CC - 1) / CC;
+    const int chunk0 = blockIdx.x * chunks_per_cta;
+    const int nloc = min(nchunks, chunk0 + chunks_per_cta) - chunk0;
+    if (nloc <= 0) return;
+    const float* g0_b = src + (size_t)bz * 2 * c * rowlen;                                  // MODE 1 only
+    const float* rows_b = MODE == 0 ? src + (size_t)bz * c * rowlen : g0_b + (size_t)c * rowlen;
+    float* dst_b = dst + (size_t)bz * c * ntargets;
+    const int* ob = offs + (size_t)bz * (ntargets + 1);
+    const int* pb = pos + (size_t)bz * rowlen;
+    auto issue = [&](int i) {
+        const int ch0 = (chunk0 + i) * CC;
+        const unsigned bytes = (unsigned)min(CC, c - ch0) * (unsigned)rowlen * 4u;
+        float* d = buf + (size_t)(i & 1) * NR * rowlen;
+        mbar_expect_tx(&bars[i & 1], MODE == 1 ? 2u * bytes : bytes);
+        if (MODE == 1) bulk_g2s(d, g0_b + (size_t)ch0 * rowlen, bytes, &bars[i & 1]);
+        bulk_g2s(d + (MODE == 1 ? CC * rowlen : 0), rows_b + (size_t)ch0 * rowlen, bytes, &bars[i & 1]);
+    };
+    if (tid == 0) {
+        mbar_init(&bars[0], 1);
+        mbar_init(&bars[1], 1);
+        mbar_fence_init();
+        nlong = 0;
     }
+    __syncthreads();
+    if (tid == 0) {
+        issue(0);
+        if (nloc > 1) issue(1);
+    }
+    const int lane = tid & 31, warp = tid >> 5;
+    // the inverse-index list of a target is the same for every chunk: thread tid keeps (up to ECACHE entries of) the
+    // list of target tid in registers, so the per-chunk work is shared-memory gathers only
+    const bool single = ntargets <= 1024;
+    int ca = 0, clen = 0, ec[ECACHE];
+    if (single && tid < ntargets) {
+        ca = ob[tid];
+        clen = ob[tid + 1] - ca;
+    }
+#pragma unroll
+    for (int u = 0; u < ECACHE; ++u) ec[u] = (single && u < clen && clen <= ECACHE) ? __ldg(pb + ca + u) : 0;
+
+    for (int i = 0; i < nloc; ++i) {
+        const int ch0 = (chunk0 + i) * CC;
+        const int cc = min(CC, c - ch0);
+        const float* stage = buf + (size_t)(i & 1) * NR * rowlen;
+        const float* rows = stage + (MODE == 1 ? CC * rowlen : 0);
+        mbar_wait(&bars[i & 1], (unsigned)((i >> 1) & 1));
+        for (int p = tid; p < ntargets; p += 1024) {
+            const int a = single ? ca : ob[p];
+            const int len = single ? clen : ob[p + 1] - a;
+            // the caller's buffer is ADDED into: read it now (coalesced), so the load latency hides under the list walk;
+            // every (channel, target) is written by exactly one thread => plain store, no atomics
+            float acc[CC], old[CC];
+#pragma unroll
+            for (int ch = 0; ch < CC; ++ch) old[ch] = ch < cc ? dst_b[(size_t)(ch0 + ch) * ntargets + p] : 0.f;
+#pragma unroll
+            for (int ch = 0; ch < CC; ++ch) {
+                acc[ch] = 0.f;
+                if (MODE == 1) {
+                    const float* r0 = stage + ch * rowlen + p * k;
+                    const float* r1 = rows + ch * rowlen + p * k;
+                    for (int s = 0; s < k; ++s) acc[ch] += r0[s] - r1[s];
+                }
+            }
+            if (single && len <= ECACHE) {
+#pragma unroll
+                for (int u = 0; u < ECACHE; ++u)
+                    if (u < len) {
+#pragma unroll
+                        for (int ch = 0; ch < CC; ++ch) acc[ch] += rows[ch * rowlen + ec[u]];
+                    }
+            } else if (len > PULL_LONG) {
+                const int slot = atomicAdd(&nlong, 1);
+                if (slot < 512) longlist[slot] = p;  // the warp pass below adds the list sum after this thread's store
+                else pull_list<CC>(pb, a, a + len, acc, [&](int ch, int e) { return rows[ch * rowlen + e]; });
+            } else {
+                pull_list<CC>(pb, a, a + len, acc, [&](int ch, int e) { return rows[ch * rowlen + e]; });
+            }
+#pragma unroll
+            for (int ch = 0; ch < CC; ++ch)
+                if (ch < cc) dst_b[(size_t)(ch0 + ch) * ntargets + p] = old[ch] + acc[ch];
+        }
+        __syncthreads();
+        const int nl = min(nlong, 512);
+        for (int j = warp; j < nl; j += 32) {
+            const int p = longlist[j];
+            float acc[CC];
+#pragma unroll
+            for (int ch = 0; ch < CC; ++ch) acc[ch] = 0.f;
+            pull_list_warp<CC>(pb, ob[p], ob[p + 1], lane, acc, [&](int ch, int e) { return rows[ch * rowlen + e]; });
+            if (lane == 0) {
+#pragma unroll
+                for (int ch = 0; ch < CC; ++ch)
+                    if (ch < cc) dst_b[(size_t)(ch0 + ch) * ntargets + p] += acc[ch];
+            }
+        }
+        __syncthreads();  // buffer (i&1) and longlist are free again
+        if (tid == 0) {
+            nlong = 0;
+            if (i + 2 < nloc) {
+                fence_proxy_async();
+                issue(i + 2);
+            }
+        }
+        __syncthreads();
+    }
+}
+
+template <int MODE>
+static int launch_pull_stream(const float* src, const int* offs, const int* pos, int b, int c, int ntargets, int rowlen, int k,
+                              float* dst, cudaStream_t st, bool* launched) {
+    *launched = false;
+    const size_t row_bytes = (size_t)rowlen * 4;
+    if ((rowlen & 3) != 0 || (reinterpret_cast<uintptr_t>(src) & 15) != 0 || 2 * row_bytes > 200 * 1024) return PDGN_OK;
+    const size_t per_cc = (MODE == 1 ? 4 : 2) * row_bytes;  // double-buffered bytes per staged channel
+    if (per_cc > 200 * 1024) return PDGN_OK;
+    const int CCsel = (4 * per_cc <= 200 * 1024 && c >= 4) ? 4 : (2 * per_cc <= 200 * 1024 && c >= 2) ? 2 : 1;
+    const int nchunks = (c + CCsel - 1) / CCsel;
+    int sms = 148;
+    int cpc = (int)(((long long)nchunks * b + 2 * sms - 1) / (2 * sms));
+    if (cpc < 1) cpc = 1;
+    dim3 grid((nchunks + cpc - 1) / cpc, b);
+    const size_t smem = (size_t)CCsel * per_cc;
+#define PDGN_LAUNCH_PULL(CC_)                                                                                                   \
+    do {                                                                                                                        \
+        PDGN_CUDA(cudaFuncSetAttribute(pull_stream_kernel<CC_, MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
+        pull_stream_kernel<CC_, MODE><<<grid, 1024, smem, st>>>(src, offs, pos, c, ntargets, rowlen, k, cpc, dst);              \
+    } while (0)
+    if (CCsel == 4) PDGN_LAUNCH_PULL(4);
+    else if (CCsel == 2) PDGN_LAUNCH_PULL(2);
+    else PDGN_LAUNCH_PULL(1);
+#undef PDGN_LAUNCH_PULL
+    PDGN_CHECK_LAUNCH();
+    *launched = true;
+    return PDGN_OK;
 }
 
 // ---------------------------------------------------------------- interpolation forward
@@ -339,7 +577,11 @@ __global__ void __launch_bounds__(GT) interp_fwd_smem_kernel(const float* __rest
     const int bz = blockIdx.z;
     const int c0 = blockIdx.y * cc_max, cc = min(cc_max, c - c0);
     const float* src = points + ((size_t)bz * c + c0) * m;
-    for (int e = threadIdx.x; e < cc * m; e += GT) rows[e] = __ldg(src + e);
+    if (((cc * m) & 3) == 0 && (reinterpret_cast<uintptr_t>(src) & 15) == 0) {
+        for (int e = threadIdx.x; e < (cc * m) >> 2; e += GT) reinterpret_cast<float4*>(rows)[e] = __ldg(reinterpret_cast<const float4*>(src) + e);
+    } else {
+        for (int e = threadIdx.x; e < cc * m; e += GT) rows[e] = __ldg(src + e);
+    }
     __syncthreads();
     const int j_end = min(n, (int)(blockIdx.x + 1) * jpart);
     float* dst0 = out + ((size_t)bz * c + c0) * n;
@@ -374,69 +616,58 @@ __global__ void __launch_bounds__(GT) interp_fwd_smem_kernel(const float* __rest
 __global__ void __launch_bounds__(512) interp_bwd_pull_kernel(const float* __restrict__ grad_out, const float* __restrict__ weight,
                                                              const int* __restrict__ offs, const int* __restrict__ pos, int c, int n,
                                                              int m, int cc_max, float* __restrict__ grad_points) {
-    extern __shared__ __align__(16) float rows[];  // [cc][n] grad_out rows, then [3n] weights
+    extern __shared__ __align__(16) float rows[];  // [cc_max][n] grad_out rows (beyond cc zero-filled), then [3n] weights
+    __shared__ int nlong, longlist[512];
     const int bz = blockIdx.y;
     const int c0 = blockIdx.x * cc_max, cc = min(cc_max, c - c0);
     const float* src = grad_out + ((size_t)bz * c + c0) * n;
+    if (threadIdx.x == 0) nlong = 0;
     for (int e = threadIdx.x; e < cc * n; e += blockDim.x) rows[e] = __ldcs(src + e);
+    for (int e = cc * n + threadIdx.x; e < cc_max * n; e += blockDim.x) rows[e] = 0.f;
     float* wsm = rows + (size_t)cc_max * n;
     const float* wsrc = weight + (size_t)bz * n * 3;
     for (int e = threadIdx.x; e < 3 * n; e += blockDim.x) wsm[e] = __ldg(wsrc + e);
     __syncthreads();
-    const int* ob = offs + (size_t)bz * (m + 1);
-    const int* pb = pos + (size_t)bz * 3 * n;
     float* dst = grad_points + ((size_t)bz * c + c0) * m;
-    for (int p = threadIdx.x; p < m; p += blockDim.x) {
-        const int a = ob[p], b = ob[p + 1];
-        float acc[8];
-#pragma unroll
-        for (int ch = 0; ch < 8; ++ch) acc[ch] = 0.f;
-        for (int q = a; q < b; ++q) {
-            const int e = __ldg(pb + q);
-            const int j = e / 3;
-            const float w = wsm[e];
-#pragma unroll
-            for (int ch = 0; ch < 8; ++ch)
-                if (ch < cc) acc[ch] += __fmul_rn(rows[ch * n + j], w);
-        }
-#pragma unroll
-        for (int ch = 0; ch < 8; ++ch)
-            if (ch < cc) dst[(size_t)ch * m + p] += acc[ch];
-    }
+    const int cm = cc_max;
+    pull_targets(offs + (size_t)bz * (m + 1), pos + (size_t)bz * 3 * n, m, cc, &nlong, longlist,
+                 [&](int ch, int e) { return ch < cm ? __fmul_rn(rows[(size_t)ch * n + e / 3], wsm[e]) : 0.f; },
+                 [&](int, int) { return 0.f; },
+                 [&](int ch, int p) { return dst + (size_t)ch * m + p; });
 }
 
 // edge features backward as a pull: grad_x[b,ch,i] += sum_s (g0[i,s] - g1[i,s]) + sum over entries e with idx[b,e] == i of g1[e]
-// (g0 = grad_ee[b,ch], g1 = grad_ee[b,c+ch], both [n*k]); the g1 row is staged in shared memory.
+// (g0 = grad_ee[b,ch], g1 = grad_ee[b,c+ch], both [n*k]); the g1 rows are staged in shared memory, g0 is read in place.
 __global__ void __launch_bounds__(512) edge_bwd_pull_kernel(const float* __restrict__ grad_ee, const int* __restrict__ offs,
                                                            const int* __restrict__ pos, int c, int n, int k, int cc_max,
                                                            float* __restrict__ grad_x) {
-    extern __shared__ __align__(16) float rows[];  // [cc][2][n*k]: g0 | g1 per channel
+    extern __shared__ __align__(16) float rows[];  // [cc_max][n*k]: g1 per channel (beyond cc zero-filled)
+    __shared__ int nlong, longlist[512];
     const int bz = blockIdx.y;
     const int c0 = blockIdx.x * cc_max, cc = min(cc_max, c - c0);
     const int nk = n * k;
-    for (int ch = 0; ch < cc; ++ch) {
-        const float* s0 = grad_ee + ((size_t)bz * 2 * c + c0 + ch) * nk;
-        const float* s1 = grad_ee + ((size_t)bz * 2 * c + c + c0 + ch) * nk;
-        float* r0 = rows + (size_t)ch * 2 * nk;
-        for (int e = threadIdx.x; e < nk; e += blockDim.x) {
-            r0[e] = __ldcs(s0 + e);
-            r0[nk + e] = __ldcs(s1 + e);
-        }
+    if (threadIdx.x == 0) nlong = 0;
+    const float* s1 = grad_ee + ((size_t)bz * 2 * c + c + c0) * nk;  // cc consecutive g1 rows are contiguous
+    if ((nk & 3) == 0) {
+        for (int e = threadIdx.x; e < cc * (nk >> 2); e += blockDim.x) reinterpret_cast<float4*>(rows)[e] = __ldcs(reinterpret_cast<const float4*>(s1) + e);
+    } else {
+        for (int e = threadIdx.x; e < cc * nk; e += blockDim.x) rows[e] = __ldcs(s1 + e);
     }
+    for (int e = cc * nk + threadIdx.x; e < cc_max * nk; e += blockDim.x) rows[e] = 0.f;
     __syncthreads();
-    const int* ob = offs + (size_t)bz * (n + 1);
-    const int* pb = pos + (size_t)bz * nk;
-    for (int i = threadIdx.x; i < n; i += blockDim.x) {
-        const int a = ob[i], b = ob[i + 1];
-        for (int ch = 0; ch < cc; ++ch) {
-            const float* r0 = rows + (size_t)ch * 2 * nk;
-            const float* r1 = r0 + nk;
-            float acc = 0.f;
-            for (int s = 0; s < k; ++s) acc += r0[i * k + s] - r1[i * k + s];
-            for (int q = a; q < b; ++q) acc += r1[__ldg(pb + q)];
-            grad_x[((size_t)bz * c + c0 + ch) * n + i] += acc;
-        }
-    }
+    const float* g0b = grad_ee + ((size_t)bz * 2 * c + c0) * nk;
+    float* dst = grad_x + ((size_t)bz * c + c0) * n;
+    const int cm = cc_max;
+    pull_targets(offs + (size_t)bz * (n + 1), pos + (size_t)bz * nk, n, cc, &nlong, longlist,
+                 [&](int ch, int e) { return ch < cm ? rows[(size_t)ch * nk + e] : 0.f; },
+                 [&](int ch, int i) {
+                     const float* g0 = g0b + (size_t)ch * nk + (size_t)i * k;
+                     const float* r1 = rows + (size_t)ch * nk + (size_t)i * k;
+                     float acc = 0.f;
+                     for (int s = 0; s < k; ++s) acc += __ldcs(g0 + s) - r1[s];
+                     return acc;
+                 },
+                 [&](int ch, int p) { return dst + (size_t)ch * n + p; });
 }
 
 // channels per CTA: keep >= ~4 waves of CTAs while amortising the index read over as many channels as possible
@@ -512,8 +743,11 @@ extern "C" int pdgn_group_bwd_ws(const float* grad_out, const int* idx, int b, i
     int* offs = reinterpret_cast<int*>(workspace);
     int* pos = offs + (size_t)b * (n + 1);
     PDGN_CUDA(cudaFuncSetAttribute(csr_build_kernel<int>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)csr_smem));
-    csr_build_kernel<int><<<b, 1024, csr_smem, st>>>(idx, n, (int)mk, offs, pos);
+    csr_build_kernel<int><<<b, CSR_T, csr_smem, st>>>(idx, n, (int)mk, offs, pos);
     PDGN_CHECK_LAUNCH();
+    bool launched = false;
+    const int rc_stream = launch_pull_stream<0>(grad_out, offs, pos, b, c, n, (int)mk, 0, grad_points, st, &launched);
+    if (rc_stream != PDGN_OK || launched) return rc_stream;
     int cc = 1;
     while (cc < 4 && (size_t)cc * 2 * row_bytes <= 100 * 1024) cc *= 2;
     const size_t smem = (size_t)cc * row_bytes;
@@ -549,6 +783,25 @@ extern "C" int pdgn_interp_fwd(const float* points, const int* idx, const float*
     if (b > 65535) return PDGN_ERR_UNSUPPORTED;
     const bool vec = (n % 4 == 0) && ((reinterpret_cast<uintptr_t>(out) | reinterpret_cast<uintptr_t>(idx) |
                                        reinterpret_cast<uintptr_t>(weight)) % 16 == 0);
+    if (vec && c >= 8 && (size_t)m * 4 * 4 <= GS_ROW_BYTES) {
+        int cc = 4;
+        while (cc * 2 <= c && (size_t)cc * 2 * m * 4 <= GS_ROW_BYTES) cc *= 2;
+        const int chunks = (c + cc - 1) / cc;
+        long long parts = (4LL * 148 * 3 + (long long)chunks * b - 1) / ((long long)chunks * b);
+        const long long max_parts = ((long long)n + GT * 4 - 1) / (GT * 4);
+        if (parts > max_parts) parts = max_parts;
+        if (parts < 1) parts = 1;
+        long long jpart = (n + parts - 1) / parts;
+        jpart = (jpart + GT * 4 - 1) / (GT * 4) * (GT * 4);
+        parts = (n + jpart - 1) / jpart;
+        const size_t smem = (size_t)cc * m * 4;
+        PDGN_CUDA(cudaFuncSetAttribute(interp_fwd_smem_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        dim3 grid((unsigned)parts, chunks, b);
+        if (grid.y > 65535) return PDGN_ERR_UNSUPPORTED;
+        interp_fwd_smem_kernel<<<grid, GT, smem, (cudaStream_t)stream>>>(points, idx, weight, c, m, n, cc, (int)jpart, out);
+        PDGN_CHECK_LAUNCH();
+        return PDGN_OK;
+    }
     const int per = vec ? 4 : 1;
     const unsigned gx = (unsigned)((n + GT * per - 1) / (GT * per));
     const int cpb = pick_cpb((long long)gx * b, c);
@@ -556,6 +809,36 @@ extern "C" int pdgn_interp_fwd(const float* points, const int* idx, const float*
     if (grid.y > 65535) return PDGN_ERR_UNSUPPORTED;
     if (vec) interp_fwd_kernel<true><<<grid, GT, 0, (cudaStream_t)stream>>>(points, idx, weight, c, m, n, cpb, out);
     else interp_fwd_kernel<false><<<grid, GT, 0, (cudaStream_t)stream>>>(points, idx, weight, c, m, n, cpb, out);
+    PDGN_CHECK_LAUNCH();
+    return PDGN_OK;
+}
+
+extern "C" size_t pdgn_interp_bwd_workspace(int b, int n, int m) {
+    if (b < 0 || n < 0 || m < 0) return 0;
+    return ((size_t)b * ((size_t)m + 1) + (size_t)b * n * 3) * sizeof(int) + 256;
+}
+
+extern "C" int pdgn_interp_bwd_ws(const float* grad_out, const int* idx, const float* weight, int b, int c, int n, int m,
+                                  float* grad_points, void* workspace, size_t workspace_bytes, void* stream) {
+    PDGN_GATHER_ARGS_OK(grad_out && idx && weight && grad_points && b >= 0 && c >= 0 && m > 0 && n >= 0);
+    if (b == 0 || c == 0 || n == 0) return PDGN_OK;
+    if (b > 65535) return PDGN_ERR_UNSUPPORTED;
+    const size_t csr_smem = ((size_t)2 * m + 32) * sizeof(int);
+    int cc = PULL_CC;
+    while (cc > 1 && ((size_t)cc * n + 3 * (size_t)n) * 4 > 96 * 1024) cc >>= 1;
+    const size_t smem = ((size_t)cc * n + 3 * (size_t)n) * 4;
+    if (!workspace || c < 4 || smem > 200 * 1024 || csr_smem > 200 * 1024 || (long long)n * 3 > 0x7fffffffLL)
+        return pdgn_interp_bwd(grad_out, idx, weight, b, c, n, m, grad_points, stream);
+    if (workspace_bytes < pdgn_interp_bwd_workspace(b, n, m) - 256 || (reinterpret_cast<uintptr_t>(workspace) & 3)) return PDGN_ERR_WORKSPACE;
+    cudaStream_t st = (cudaStream_t)stream;
+    int* offs = reinterpret_cast<int*>(workspace);
+    int* pos = offs + (size_t)b * (m + 1);
+    PDGN_CUDA(cudaFuncSetAttribute(csr_build_kernel<int>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)csr_smem));
+    csr_build_kernel<int><<<b, CSR_T, csr_smem, st>>>(idx, m, 3 * n, offs, pos);
+    PDGN_CHECK_LAUNCH();
+    PDGN_CUDA(cudaFuncSetAttribute(interp_bwd_pull_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    dim3 grid((c + cc - 1) / cc, b);
+    interp_bwd_pull_kernel<<<grid, 512, smem, st>>>(grad_out, weight, offs, pos, c, n, m, cc, grad_points);
     PDGN_CHECK_LAUNCH();
     return PDGN_OK;
 }
@@ -602,6 +885,41 @@ extern "C" int pdgn_edge_feat_bwd(const float* grad_ee, const int64_t* idx, int 
     dim3 grid(gx, (c + cpb - 1) / cpb, b);
     if (grid.y > 65535) return PDGN_ERR_UNSUPPORTED;
     edge_bwd_kernel<<<grid, GT, 0, (cudaStream_t)stream>>>(grad_ee, reinterpret_cast<const long long*>(idx), c, n, k, cpb, grad_x);
+    PDGN_CHECK_LAUNCH();
+    return PDGN_OK;
+}
+
+extern "C" size_t pdgn_edge_feat_bwd_workspace(int b, int n, int k) {
+    if (b < 0 || n < 0 || k < 0) return 0;
+    return ((size_t)b * ((size_t)n + 1) + (size_t)b * n * k) * sizeof(int) + 256;
+}
+
+extern "C" int pdgn_edge_feat_bwd_ws(const float* grad_ee, const int64_t* idx, int b, int c, int n, int k, float* grad_x,
+                                     void* workspace, size_t workspace_bytes, void* stream) {
+    PDGN_GATHER_ARGS_OK(grad_ee && idx && grad_x && b >= 0 && c >= 0 && n >= 0 && k >= 0);
+    if (b == 0 || c == 0 || n == 0 || k == 0) return PDGN_OK;
+    if (b > 65535) return PDGN_ERR_UNSUPPORTED;
+    const long long nk = (long long)n * k;
+    const size_t csr_smem = ((size_t)2 * n + 32) * sizeof(int);
+    const size_t row_bytes = (size_t)nk * 4;  // the g1 row of one channel
+    if (!workspace || row_bytes > 200 * 1024 || csr_smem > 200 * 1024 || nk > 0x7fffffffLL)
+        return pdgn_edge_feat_bwd(grad_ee, idx, b, c, n, k, grad_x, stream);
+    if (workspace_bytes < pdgn_edge_feat_bwd_workspace(b, n, k) - 256 || (reinterpret_cast<uintptr_t>(workspace) & 3)) return PDGN_ERR_WORKSPACE;
+    cudaStream_t st = (cudaStream_t)stream;
+    int* offs = reinterpret_cast<int*>(workspace);
+    int* pos = offs + (size_t)b * (n + 1);
+    PDGN_CUDA(cudaFuncSetAttribute(csr_build_kernel<long long>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)csr_smem));
+    csr_build_kernel<long long><<<b, CSR_T, csr_smem, st>>>(reinterpret_cast<const long long*>(idx), n, (int)nk, offs, pos);
+    PDGN_CHECK_LAUNCH();
+    bool launched = false;
+    const int rc_stream = launch_pull_stream<1>(grad_ee, offs, pos, b, c, n, (int)nk, k, grad_x, st, &launched);
+    if (rc_stream != PDGN_OK || launched) return rc_stream;
+    int cc = 1;
+    while (cc < 4 && (size_t)cc * 2 * row_bytes <= 100 * 1024) cc *= 2;
+    const size_t smem = (size_t)cc * row_bytes;
+    PDGN_CUDA(cudaFuncSetAttribute(edge_bwd_pull_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    dim3 grid((c + cc - 1) / cc, b);
+    edge_bwd_pull_kernel<<<grid, 512, smem, st>>>(grad_ee, offs, pos, c, n, k, cc, grad_x);
     PDGN_CHECK_LAUNCH();
     return PDGN_OK;
 }

@@ -87,8 +87,12 @@ def interp_bwd(grad_out, idx, weight, m):
     _req(grad_out, "grad_out"); _req(idx, "idx", torch.int32); _req(weight, "weight")
     b, c, n = grad_out.shape
     grad = torch.zeros((b, c, m), dtype=torch.float32, device=grad_out.device)
+    L = lib()
+    ws_bytes = L.pdgn_interp_bwd_workspace(b, n, m)
+    ws = torch.empty((ws_bytes,), dtype=torch.uint8, device=grad_out.device)
     with torch.cuda.device(grad_out.device):
-        check(lib().pdgn_interp_bwd(grad_out.data_ptr(), idx.data_ptr(), weight.data_ptr(), b, c, n, m, grad.data_ptr(), _stream(grad_out)), "pdgn_interp_bwd")
+        check(L.pdgn_interp_bwd_ws(grad_out.data_ptr(), idx.data_ptr(), weight.data_ptr(), b, c, n, m, grad.data_ptr(), ws.data_ptr(),
+                                   ws_bytes, _stream(grad_out)), "pdgn_interp_bwd_ws")
     return grad
 
 
@@ -185,6 +189,10 @@ def edge_feat_bwd(grad_ee, idx, c):
     _req(grad_ee, "grad_ee"); _req(idx, "idx", torch.int64)
     b, _, n, k = grad_ee.shape
     gx = torch.zeros((b, c, n), dtype=torch.float32, device=grad_ee.device)
+    L = lib()
+    ws_bytes = L.pdgn_edge_feat_bwd_workspace(b, n, k)
+    ws = torch.empty((ws_bytes,), dtype=torch.uint8, device=grad_ee.device)
     with torch.cuda.device(grad_ee.device):
-        check(lib().pdgn_edge_feat_bwd(grad_ee.data_ptr(), idx.data_ptr(), b, c, n, k, gx.data_ptr(), _stream(grad_ee)), "pdgn_edge_feat_bwd")
+        check(L.pdgn_edge_feat_bwd_ws(grad_ee.data_ptr(), idx.data_ptr(), b, c, n, k, gx.data_ptr(), ws.data_ptr(), ws_bytes,
+                                      _stream(grad_ee)), "pdgn_edge_feat_bwd_ws")
     return gx
