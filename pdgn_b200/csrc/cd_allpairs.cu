@@ -66,25 +66,36 @@ extern "C" int pdgn_cd_allpairs(const float* A, const float* B, int na, int nb, 
     float* PA = reinterpret_cast<float*>(workspace);
     float* PB = PA + (size_t)nrows * 3 * npad;
 
+    // same set against itself (the rr / ss matrices of compute_all_metrics, evaluation_metrics.py:187-188): pack once,
+    // compute the upper triangle, mirror it
+    const bool sym = (A == B) && row0 == col0 && row1 == col1 && nrows > 1;
     dim3 pb(256), pga((npad + 255) / 256, nrows), pgb((npad + 255) / 256, ncols);
     cd_pack_kernel<<<pga, pb, 0, st>>>(A, row0, npts, npad, PA);
     PDGN_CHECK_LAUNCH();
-    cd_pack_kernel<<<pgb, pb, 0, st>>>(B, col0, npts, npad, PB);
-    PDGN_CHECK_LAUNCH();
+    if (sym) {
+        PB = PA;
+    } else {
+        cd_pack_kernel<<<pgb, pb, 0, st>>>(B, col0, npts, npad, PB);
+        PDGN_CHECK_LAUNCH();
+    }
 
     const size_t smem = cd_smem_bytes<CD_NH, CD_VARIANT>(npad);
     PDGN_CUDA(cudaFuncSetAttribute(PDGN_CD_KERNEL, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     const int spairs = (nrows + CD_NH - 1) / CD_NH;
     if (spairs > 65535) return PDGN_ERR_UNSUPPORTED;
     // enough CTAs for >= ~20 waves of 2 CTAs/SM so the tail is small; each CTA walks `rstrip` B clouds
-    const int target = 20 * CD_MINB * cd_num_sms();
+    const int target = (sym ? 40 : 20) * CD_MINB * cd_num_sms();  // sym: about half the CTAs exit immediately
     int strips = (target + spairs - 1) / spairs;
     if (strips > ncols) strips = ncols;
     if (strips < 1) strips = 1;
     const int rstrip = (ncols + strips - 1) / strips;
     strips = (ncols + rstrip - 1) / rstrip;
-    PDGN_CD_KERNEL<<<dim3(strips, spairs), CD_THREADS, smem, st>>>(PA, PB, nrows, ncols, npts, npad, rstrip, out, ld_out);
+    PDGN_CD_KERNEL<<<dim3(strips, spairs), CD_THREADS, smem, st>>>(PA, PB, nrows, ncols, npts, npad, rstrip, sym ? 1 : 0, out, ld_out);
     PDGN_CHECK_LAUNCH();
+    if (sym) {
+        cd_mirror_kernel<<<dim3((nrows + 31) / 32, (nrows + 7) / 8), dim3(32, 8), 0, st>>>(out, nrows, ld_out);
+        PDGN_CHECK_LAUNCH();
+    }
     return PDGN_OK;
 }
 

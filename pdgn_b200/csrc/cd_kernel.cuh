@@ -108,7 +108,7 @@ __device__ __forceinline__ void cd_two_candidates_aos(const float (&qx)[R], cons
 template <int R, int NH, int MINB, int VAR>
 __global__ void __launch_bounds__(NH * CD_HALF, MINB)
 cd_allpairs_kernel(const float* __restrict__ PA, const float* __restrict__ PB, int nrows, int ncols, int npts, int npad,
-                   int rstrip, float* __restrict__ out, long long ld_out) {
+                   int rstrip, int sym, float* __restrict__ out, long long ld_out) {
     constexpr int ROWS = R * CD_HALF;
     extern __shared__ __align__(128) unsigned char smem_raw[];
     constexpr int STAGE = ((VAR & CDV_AOS) ? 4 : 3) * CD_TILE;                // floats per stage
@@ -121,8 +121,11 @@ cd_allpairs_kernel(const float* __restrict__ PA, const float* __restrict__ PB, i
     int s = blockIdx.y * NH + half;
     const bool s_valid = s < nrows;
     if (!s_valid) s = nrows - 1;  // ragged row count: spare halves recompute the last cloud and discard it
-    const int r_begin = blockIdx.x * rstrip;
-    const int r_end = min(ncols, r_begin + rstrip);
+    // sym: A and B are the same cloud set => CD(s,r) == CD(r,s); this CTA only walks r >= its first row, the lower
+    // triangle is filled by cd_mirror_kernel afterwards (saves ~half the work of the rr / ss matrices)
+    const int r_begin = sym ? max((int)(blockIdx.x * rstrip), (int)(blockIdx.y * NH)) : blockIdx.x * rstrip;
+    const int r_end = min(ncols, (int)(blockIdx.x * rstrip) + rstrip);
+    if (r_begin >= r_end) return;
     const int nrb = (npts + ROWS - 1) / ROWS;
     const int ncb = (npad + CD_TILE - 1) / CD_TILE;
     const int ntiles = (r_end - r_begin) * nrb * ncb;
@@ -247,6 +250,12 @@ cd_allpairs_kernel(const float* __restrict__ PA, const float* __restrict__ PB, i
             out[(size_t)s * ld_out + r] = (rr[0] + rr[1] + rr[2] + rr[3]) * inv_n;
         }
     }
+}
+
+// out[r][s] = out[s][r] for r > s (square matrix)
+__global__ void cd_mirror_kernel(float* __restrict__ out, int n, long long ld) {
+    const int r = blockIdx.y * blockDim.y + threadIdx.y, s = blockIdx.x * blockDim.x + threadIdx.x;
+    if (r < n && s < r) out[(size_t)r * ld + s] = out[(size_t)s * ld + r];
 }
 
 template <int NH, int VAR = 0>

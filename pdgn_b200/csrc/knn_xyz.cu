@@ -121,13 +121,14 @@ __device__ __forceinline__ void ks_load_tile(float* tile, const float* __restric
 
 // per-warp shared block
 template <int G>
-struct KsWarp {
+struct alignas(16) KsWarp {
     unsigned short sub[KS_NSUB][32];   // [subgroup][(query + subgroup) & 31]  bf16, rounded down  (swizzled: both the
                                        //   lane=query writes and the lane=subgroup reads are bank-conflict free)
     unsigned short grp[G][32];         // [group][query]  bf16, rounded up
     unsigned long long key[KS_SCAP];   // survivors of the query being selected: (d2 bits << 32) | candidate index --
                                        //   d2 >= 0, so unsigned order of the key == the reference's (d2, index) order
     unsigned short plist[KS_NSUB];     // subgroups that may hold survivors
+    int nsurv;                         // survivor counter of the query being selected
 };
 
 template <int G, int NWARPS>
@@ -224,9 +225,11 @@ __global__ void __launch_bounds__(NWARPS * 32) knn_select_kernel(const float* __
             npass += __popc(mask);
         }
         __syncwarp();
-        // rescan those subgroups: 4 consecutive candidates per lane, 128 per step; survivors compacted in index order
+        // rescan those subgroups: 4 consecutive candidates per lane, 128 per step.  Survivors are appended in ANY order
+        // (shared-memory counter): their 64-bit (d2, index) keys are unique, so the ranking below does not need them sorted.
         const int total = npass << log2ss;
-        int nsurv = 0;
+        if (lane == 0) wsm->nsurv = 0;
+        __syncwarp();
         for (int p0 = 0; p0 < total; p0 += 128) {
             const int p = p0 + 4 * lane;
             const bool ok = p < total;
@@ -251,27 +254,17 @@ __global__ void __launch_bounds__(NWARPS * 32) knn_select_kernel(const float* __
                     }
                 }
             }
-            bool keep[4];
-            int below = 0, mine = 0;  // survivors in lower lanes / in this lane so far
-            unsigned all = 0;
 #pragma unroll
             for (int u = 0; u < 4; ++u) {
-                keep[u] = ok && j + u < n && d[u] <= tq && d[u] < kInf;  // NaN and +inf never survive; j+u >= n: ragged subgroup
-                const unsigned mask = __ballot_sync(kFull, keep[u]);
-                below += __popc(mask & lt);
-                all += __popc(mask);
-            }
-#pragma unroll
-            for (int u = 0; u < 4; ++u) {
-                if (keep[u]) {
-                    const int pos = nsurv + below + mine;
+                // NaN and +inf never survive; j+u >= n: ragged last subgroup
+                if (ok && j + u < n && d[u] <= tq && d[u] < kInf) {
+                    const int pos = atomicAdd(&wsm->nsurv, 1);
                     if (pos < KS_SCAP) wsm->key[pos] = ((unsigned long long)__float_as_uint(d[u]) << 32) | (unsigned)(j + u);
-                    ++mine;
                 }
             }
-            nsurv += all;
         }
         __syncwarp();
+        const int nsurv = wsm->nsurv;
         int* oi = idx + ((size_t)bz * m + q0 + qi) * k;
         float* od = dist2 ? dist2 + ((size_t)bz * m + q0 + qi) * k : nullptr;
         if (nsurv <= KS_SCAP) {

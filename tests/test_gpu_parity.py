@@ -247,6 +247,21 @@ def test_cd_allpairs_tiles_and_host_path(dev):
     np.testing.assert_array_equal(host_tile.numpy(), full[1:4, 2:9])
 
 
+@pytest.mark.parametrize("n,npts", [(7, 256), (2, 100), (33, 64), (12, 2048)])
+def test_cd_allpairs_same_set_uses_symmetry(dev, n, npts):
+    """A against itself (the rr / ss matrices): upper triangle + mirror must equal the full computation."""
+    from oracle import cpu as ocpu
+    from pdgn_b200 import ops
+    rng = np.random.default_rng(n * 7 + npts)
+    A = clouds_sphere(rng, n, npts, 3)
+    dA = G(A, dev)
+    sym = C(ops.cd_allpairs(dA, dA))
+    full = C(ops.cd_allpairs(dA, dA.clone()))  # different pointer => general path
+    np.testing.assert_allclose(sym, ocpu.cd_allpairs(A, A), rtol=2e-6, atol=1e-9)
+    np.testing.assert_allclose(sym, full, rtol=2e-6, atol=1e-9)
+    assert np.array_equal(sym, sym.T) and np.all(np.diag(sym) == 0)
+
+
 def test_pairwise_and_metrics_match_reference_golden(dev, golden):
     """_pairwise_EMD_CD_ and compute_all_metrics against what the reference's own code produced (CD keys)."""
     from pdgn_b200 import evaluation_metrics as em
