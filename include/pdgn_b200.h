@@ -113,6 +113,15 @@ int pdgn_cd_allpairs(const float *A, const float *B, int na, int nb, int npts, i
 int pdgn_cd_allpairs_host(const float *A_host, const float *B_host, int na, int nb, int npts, int row0, int row1,
                           int col0, int col1, float *out_host, long long ld_out, void *stream);
 
+/* ---- all-pairs approximate Earth Mover's Distance -------------------------------------------------------
+ * Replaces, for evaluation, ApproxMatch + MatchCost (evaluation/pytorch_structural_losses/src/approxmatch.cu:3-224,
+ * bound as StructuralLossesBackend.ApproxMatch / MatchCost, pybind/bind.cpp:10-16) as emd_approx composes them
+ * (evaluation/evaluation_metrics.py:26-31) inside _pairwise_EMD_CD_ (:110).  A [na,n,3], B [nb,m,3] ->
+ *   out[(s-row0)*ld_out + (r-col0)] = match_cost(A_s, B_r) / n.
+ * The n x m match matrix is never materialised.  n, m <= 2048.  No gradient (evaluation only). */
+int pdgn_emd_allpairs(const float *A, const float *B, int na, int nb, int n, int m, int row0, int row1, int col0,
+                      int col1, float *out, long long ld_out, void *stream);
+
 /* ---- feature-space kNN of the generator ---------------------------------------------------------------
  * Replaces bmm + torch.sort + slice in get_edge_features{,_xyz} (models/PDGNet_v2.py:449-459, :492-502).
  * x [b,c,n] -> idx int64 [b,n,k]: ranks skip..skip+k-1 of the ascending (d2, index) order of exact FP32

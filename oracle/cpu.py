@@ -146,3 +146,24 @@ def knn_feat(x, k, skip=1):
     d2, pd = _out((b, n, k), np.float32)
     lib().oracle_knn_feat(px, b, c, n, k, skip, pi, pd)
     return idx, d2
+
+
+def emd_cost(xyz1, xyz2):
+    """Approximate-EMD matching cost per pair, xyz1 [b,n,3] vs xyz2 [b,m,3] -> [b] (approxmatch.cu + matchcost)."""
+    xyz1, p1 = _f(xyz1)
+    xyz2, p2 = _f(xyz2)
+    b, n, _ = xyz1.shape
+    m = xyz2.shape[1]
+    out, po = _out((b,), np.float32)
+    lib().oracle_emd_cost(p1, p2, b, n, m, po)
+    return out
+
+
+def emd_allpairs(A, B):
+    """all_emd[s, r] = match_cost(A_s, B_r) / npts (evaluation_metrics.py:26-31, :110)."""
+    A = np.ascontiguousarray(A, dtype=np.float32)
+    B = np.ascontiguousarray(B, dtype=np.float32)
+    na, nb, npts = A.shape[0], B.shape[0], A.shape[1]
+    x1 = np.repeat(A, nb, axis=0)
+    x2 = np.tile(B, (na, 1, 1))
+    return (emd_cost(x1, x2) / np.float32(npts)).reshape(na, nb)

@@ -8,7 +8,7 @@
  * Parity status: the reference ships no tests or golden vectors for this path, so
  * the arithmetic here is pinned by (i) the SASS of the reference kernels recompiled with nvcc 12.9 for
  * sm_100a (see oracle/Makefile target `ref`; the FMUL/FFMA order below was read from cuobjdump) and
- * (ii) tests/test_ref_kernels.py, which runs those recompiled reference kernels (oracle/_ref) on the
+ * (ii) tests/test_gpu_parity.py, which runs those recompiled reference kernels (oracle/_ref) on the
  * GPU box against this file bit for bit.
  *
  * Build: gcc -O2 -ffp-contract=off -fopenmp -shared -fPIC (no contraction by the host compiler: every
@@ -253,3 +253,60 @@ void oracle_knn_feat(const float *x, int b, int c, int n, int k, int skip, int64
 }
 
 int oracle_abi_version(void) { return 1; }
+
+/* Approximate EMD (auction-style matching) and its cost, restated from
+ * evaluation/pytorch_structural_losses/src/approxmatch.cu:3-182 (approxmatchkernel) and :184-224 (matchcostkernel),
+ * as MatchCostFunction.forward composes them (match_cost.py:11-24): cost[i] = sum_{k,l} match[l][k] * |xyz1_k - xyz2_l|.
+ * The match matrix is linear in the per-level weights, so the cost is accumulated level by level and the n x m matrix is
+ * never stored.  Arithmetic is FP32 with expf() where the kernel uses __expf (fast intrinsic) and sequential sums where
+ * the kernel sums tile by tile: parity is by tolerance (tests use 2e-4 relative), not bit-exact.
+ * xyz1 [b,n,3], xyz2 [b,m,3] -> cost [b].  (emd_approx divides by n afterwards, evaluation_metrics.py:26-31.) */
+void oracle_emd_cost(const float *xyz1, const float *xyz2, int b, int n, int m, float *cost) {
+#pragma omp parallel for schedule(dynamic, 1)
+    for (int i = 0; i < b; ++i) {
+        const float *P = xyz1 + (long)i * n * 3, *Q = xyz2 + (long)i * m * 3;
+        float *remainL = (float *)malloc(sizeof(float) * (size_t)(2 * n + 2 * m));
+        float *remainR = remainL + n, *ratioL = remainR + m, *ratioR = ratioL + n;
+        const float multiL = n >= m ? 1.f : (float)(m / n), multiR = n >= m ? (float)(n / m) : 1.f;
+        for (int k = 0; k < n; ++k) remainL[k] = multiL;
+        for (int l = 0; l < m; ++l) remainR[l] = multiR;
+        double total = 0.0;
+        for (int j = 7; j > -2; --j) {
+            const float level = -powf(4.0f, (float)j);
+            for (int k = 0; k < n; ++k) {
+                float suml = 1e-9f;
+                for (int l = 0; l < m; ++l) {
+                    const float dx = Q[l * 3] - P[k * 3], dy = Q[l * 3 + 1] - P[k * 3 + 1], dz = Q[l * 3 + 2] - P[k * 3 + 2];
+                    suml += expf(level * (dx * dx + dy * dy + dz * dz)) * remainR[l];
+                }
+                ratioL[k] = remainL[k] / suml;
+            }
+            for (int l = 0; l < m; ++l) {
+                float sumr = 0.f;
+                for (int k = 0; k < n; ++k) {
+                    const float dx = Q[l * 3] - P[k * 3], dy = Q[l * 3 + 1] - P[k * 3 + 1], dz = Q[l * 3 + 2] - P[k * 3 + 2];
+                    sumr += expf(level * (dx * dx + dy * dy + dz * dz)) * ratioL[k];
+                }
+                sumr *= remainR[l];
+                const float consumption = fminf(remainR[l] / (sumr + 1e-9f), 1.0f);
+                ratioR[l] = consumption * remainR[l];
+                remainR[l] = fmaxf(0.0f, remainR[l] - sumr);
+            }
+            for (int k = 0; k < n; ++k) {
+                float suml = 0.f;
+                double c = 0.0;
+                for (int l = 0; l < m; ++l) {
+                    const float dx = Q[l * 3] - P[k * 3], dy = Q[l * 3 + 1] - P[k * 3 + 1], dz = Q[l * 3 + 2] - P[k * 3 + 2];
+                    const float d2 = dx * dx + dy * dy + dz * dz;
+                    const float w = expf(level * d2) * ratioL[k] * ratioR[l];
+                    suml += w;
+                    c += (double)w * (double)sqrtf(d2);
+                }
+                remainL[k] = fmaxf(0.0f, remainL[k] - suml);
+                total += c;
+            }
+        }
+        cost[i] = (float)total;
+        free(remainL);
+    }
+}

@@ -99,3 +99,18 @@ def nndistance(xyz1, xyz2):
     torch.cuda.synchronize()
     assert rc == 0, rc
     return d1, i1, d2, i2
+
+
+def match_cost(xyz1, xyz2):
+    """[b] approximate-EMD matching cost through the reference's approxmatch + matchcost kernels."""
+    b, n, _ = xyz1.shape
+    m = xyz2.shape[1]
+    dev = xyz1.device
+    match = torch.zeros((b, m, n), dtype=torch.float32, device=dev)
+    temp = torch.zeros((b, (n + m) * 2), dtype=torch.float32, device=dev)
+    out = torch.zeros((b,), dtype=torch.float32, device=dev)
+    torch.cuda.synchronize()
+    rc = lib().ref_match_cost(b, n, m, _p(xyz1), _p(xyz2), _p(match), _p(temp), _p(out), ctypes.c_void_p(0))
+    torch.cuda.synchronize()
+    assert rc == 0, rc
+    return out

@@ -11,7 +11,21 @@ void nndistancegrad(int b, int n, const float *xyz1, int m, const float *xyz2, c
                     const int *idx1, const float *grad_dist2, const int *idx2, float *grad_xyz1,
                     float *grad_xyz2, cudaStream_t stream);
 
+void approxmatch(int b, int n, int m, const float *xyz1, const float *xyz2, float *match, float *temp, cudaStream_t stream);
+void matchcost(int b, int n, int m, const float *xyz1, const float *xyz2, float *match, float *out, cudaStream_t stream);
+
 extern "C" {
+// ApproxMatch + MatchCost as MatchCostFunction.forward chains them (match_cost.py:21-23).
+// match: [b, m, n] scratch, temp: [b, (n+m)*2] scratch, out: [b].
+int ref_match_cost(int b, int n, int m, const float *xyz1, const float *xyz2, float *match, float *temp, float *out, void *stream) {
+    try {
+        approxmatch(b, n, m, xyz1, xyz2, match, temp, (cudaStream_t)stream);
+        matchcost(b, n, m, xyz1, xyz2, match, out, (cudaStream_t)stream);
+    } catch (...) {
+        return -1;
+    }
+    return (int)cudaGetLastError();
+}
 int ref_nndistance(int b, int n, const float *xyz, int m, const float *xyz2, float *d1, int *i1, float *d2, int *i2,
                    void *stream) {
     nndistance(b, n, xyz, m, xyz2, d1, i1, d2, i2, (cudaStream_t)stream);

@@ -51,6 +51,11 @@ def max_tile(world, n_rows, n_cols):
     return -(-n_rows // pr), -(-n_cols // pc)
 
 
+def pairwise_emd(sample_pcs, ref_pcs, group=None):
+    """Full [N_sample, N_ref] approximate-EMD matrix on every rank (same tiling and collective as pairwise_cd)."""
+    return pairwise_cd(sample_pcs, ref_pcs, group=group, compute_tile=ops.emd_allpairs)
+
+
 def pairwise_cd(sample_pcs, ref_pcs, group=None, compute_tile=None):
     """Full [N_sample, N_ref] Chamfer matrix on every rank.  `compute_tile(sample, ref, rows, cols)` defaults to
     the CUDA kernel; tests substitute a CPU function to exercise the tiling + collective with gloo."""

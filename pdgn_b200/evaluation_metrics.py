@@ -7,9 +7,12 @@ pointed here (pdgn_b200.dropin).  What changes is where the work happens:
     Under torch.distributed the matrix is 2-D tiled over the ranks (pdgn_b200.dist).
   * distChamfer / distChamferCUDA (:35-45, :22-23): the paired min-distance kernel (csrc/chamfer.cu).
   * lgan_mmd_cov, knn, compute_all_metrics (:125-200): unchanged torch reductions on the [N,N] matrices.
-Approximate EMD (approxmatch.cu) is outside this round's scope: all_emd is returned
-as None and the *-EMD keys are omitted; DESIGN.md states this.
+  * emd_approx / match_cost (:26-31, match_cost.py) and the EMD half of _pairwise_EMD_CD_: the all-pairs approximate-EMD
+    kernel (csrc/emd.cu), forward only -- the reference uses EMD only in evaluation.
+Set PDGN_B200_SKIP_EMD=1 to skip the EMD matrices (they cost ~35x the CD ones): all_emd is then None and the *-EMD keys
+are omitted.
 """
+import os
 import warnings
 
 import torch
@@ -29,9 +32,26 @@ def distChamfer(a, b):
     return m_ba, m_ab
 
 
+def match_cost(seta, setb):
+    """match_cost.py:6-44, forward only: per-pair approximate-EMD matching cost [B] of seta [B,n,3] vs setb [B,m,3]."""
+    seta = seta.detach().contiguous().float()
+    setb = setb.detach().contiguous().float()
+    n = seta.size(1)
+    out = torch.empty((seta.size(0),), dtype=torch.float32, device=seta.device)
+    for i in range(seta.size(0)):  # paired form = diagonal of the all-pairs problem, one 1x1 tile per pair
+        out[i:i + 1] = ops.emd_allpairs(seta, setb, rows=(i, i + 1), cols=(i, i + 1)).view(1) * float(n)
+    return out
+
+
 def emd_approx(sample, ref):
-    raise NotImplementedError("approximate EMD (evaluation/pytorch_structural_losses/src/approxmatch.cu) is a next-row item "
-                              "(SURVEY.md section 8f); only the CD metrics are implemented")
+    """evaluation_metrics.py:26-31: match_cost / N."""
+    B, N, N_ref = sample.size(0), sample.size(1), ref.size(1)
+    assert N == N_ref, "Not sure what would EMD do in this case"
+    return match_cost(sample, ref) / float(N)
+
+
+def _skip_emd():
+    return os.environ.get("PDGN_B200_SKIP_EMD", "0") not in ("", "0")
 
 
 def EMD_CD(sample_pcs, ref_pcs, batch_size, accelerated_cd=False, reduced=True):
@@ -44,17 +64,21 @@ def EMD_CD(sample_pcs, ref_pcs, batch_size, accelerated_cd=False, reduced=True):
         dl, dr = distChamfer(sample_pcs[b_start:b_end].contiguous(), ref_pcs[b_start:b_end].contiguous())
         cd_lst.append(dl.mean(dim=1) + dr.mean(dim=1))
     cd = torch.cat(cd_lst).mean() if reduced else torch.cat(cd_lst)
-    return {"MMD-CD": cd}
+    if _skip_emd():
+        return {"MMD-CD": cd}
+    emd = emd_approx(sample_pcs.contiguous(), ref_pcs.contiguous())
+    return {"MMD-CD": cd, "MMD-EMD": emd.mean() if reduced else emd}
 
 
 def _pairwise_EMD_CD_(sample_pcs, ref_pcs, batch_size=None, accelerated_cd=True):
-    """evaluation_metrics.py:85-121.  Returns (all_cd [N_sample, N_ref], all_emd=None)."""
+    """evaluation_metrics.py:85-121.  Returns (all_cd, all_emd), both [N_sample, N_ref] (all_emd None if skipped)."""
     from . import dist
     sample_pcs = sample_pcs.contiguous().float()
     ref_pcs = ref_pcs.contiguous().float()
+    skip = _skip_emd()
     if dist.is_distributed():
-        return dist.pairwise_cd(sample_pcs, ref_pcs), None
-    return ops.cd_allpairs(sample_pcs, ref_pcs), None
+        return dist.pairwise_cd(sample_pcs, ref_pcs), (None if skip else dist.pairwise_emd(sample_pcs, ref_pcs))
+    return ops.cd_allpairs(sample_pcs, ref_pcs), (None if skip else ops.emd_allpairs(sample_pcs, ref_pcs))
 
 
 def knn(Mxx, Mxy, Myy, k, sqrt=False):
@@ -103,10 +127,15 @@ def compute_all_metrics(sample_pcs, ref_pcs, batch_size=None, accelerated_cd=Fal
     results = {}
     M_rs_cd, M_rs_emd = _pairwise_EMD_CD_(sample_pcs, ref_pcs, batch_size, accelerated_cd=accelerated_cd)
     results.update({"%s-CD" % k: v for k, v in lgan_mmd_cov(M_rs_cd.t()).items()})
+    if M_rs_emd is not None:
+        results.update({"%s-EMD" % k: v for k, v in lgan_mmd_cov(M_rs_emd.t()).items()})
     M_rr_cd, M_rr_emd = _pairwise_EMD_CD_(ref_pcs, ref_pcs, batch_size, accelerated_cd=accelerated_cd)
     M_ss_cd, M_ss_emd = _pairwise_EMD_CD_(sample_pcs, sample_pcs, batch_size, accelerated_cd=accelerated_cd)
     one_nn_cd_res = knn(M_rr_cd, M_rs_cd, M_ss_cd, 1, sqrt=False)
     results.update({"1-NN-CD-%s" % k: v for k, v in one_nn_cd_res.items() if "acc" in k})
-    if M_rs_emd is None:
-        warnings.warn("pdgn_b200: EMD metrics are not implemented; only the -CD keys are returned", stacklevel=2)
+    if M_rs_emd is not None:
+        one_nn_emd_res = knn(M_rr_emd, M_rs_emd, M_ss_emd, 1, sqrt=False)
+        results.update({"1-NN-EMD-%s" % k: v for k, v in one_nn_emd_res.items() if "acc" in k})
+    else:
+        warnings.warn("pdgn_b200: PDGN_B200_SKIP_EMD is set; only the -CD keys are returned", stacklevel=2)
     return results

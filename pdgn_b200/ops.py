@@ -147,6 +147,21 @@ def cd_allpairs(A, B, rows=None, cols=None, out=None):
     return out
 
 
+def emd_allpairs(A, B, rows=None, cols=None, out=None):
+    """Approximate-EMD matrix tile: A [na,n,3], B [nb,m,3] -> [rows, cols] of match_cost / n (no gradient)."""
+    _req(A, "A"); _req(B, "B")
+    na, n, _ = A.shape
+    nb, m, _ = B.shape
+    r0, r1 = rows if rows is not None else (0, na)
+    c0, c1 = cols if cols is not None else (0, nb)
+    if out is None:
+        out = torch.empty((r1 - r0, c1 - c0), dtype=torch.float32, device=A.device)
+    with torch.cuda.device(A.device):
+        check(lib().pdgn_emd_allpairs(A.data_ptr(), B.data_ptr(), na, nb, n, m, r0, r1, c0, c1, out.data_ptr(), out.stride(0),
+                                      _stream(A)), "pdgn_emd_allpairs")
+    return out
+
+
 def cd_allpairs_host(A, B, rows=None, cols=None):
     """Same, for CPU (ideally pinned) tensors: H2D + kernel + D2H inside the C call; returns a CPU tensor."""
     if A.is_cuda or B.is_cuda:

@@ -268,14 +268,21 @@ def test_pairwise_and_metrics_match_reference_golden(dev, golden):
     g = golden("evaluation_metrics")
     smp, ref = G(g["smp"], dev), G(g["ref"], dev)
     all_cd, all_emd = em._pairwise_EMD_CD_(smp, ref, 4)
-    assert all_emd is None
+    assert tuple(all_emd.shape) == tuple(all_cd.shape)
     np.testing.assert_allclose(C(all_cd), g["all_cd"], rtol=1e-5, atol=1e-7)
-    with pytest.warns(UserWarning):
-        res = em.compute_all_metrics(smp, ref, 4)
+    res = em.compute_all_metrics(smp, ref, 4)
     keys = [k[len("metric:"):] for k in g.files if k.startswith("metric:")]
-    assert sorted(res) == sorted(keys)
+    assert sorted(res) == sorted(keys + [k.replace("-CD", "-EMD") for k in keys])  # the reference's full key set
     for k in keys:
         assert res[k].item() == pytest.approx(float(g["metric:" + k]), rel=1e-5, abs=1e-9), k
+    monkey = pytest.MonkeyPatch()
+    monkey.setenv("PDGN_B200_SKIP_EMD", "1")
+    try:
+        with pytest.warns(UserWarning):
+            res_cd = em.compute_all_metrics(smp, ref, 4)
+        assert sorted(res_cd) == sorted(keys)
+    finally:
+        monkey.undo()
 
 
 def test_cd_allpairs_full_size_properties(dev):
@@ -295,6 +302,40 @@ def test_cd_allpairs_full_size_properties(dev):
     for s, r in pick:
         ref = ocpu.cd_allpairs(A[s:s + 1], B[r:r + 1])[0, 0]
         assert abs(M[s, r] - ref) <= 2e-6 * ref
+
+
+# ------------------------------------------------------------------------------------------------ approximate EMD
+@pytest.mark.parametrize("na,nb,n,m,maker", [(3, 4, 256, 256, clouds_uniform), (2, 2, 2048, 2048, clouds_sphere), (2, 3, 300, 300, clouds_uniform),
+                                             (2, 2, 512, 256, clouds_uniform), (1, 2, 100, 400, clouds_sphere)])
+def test_emd_allpairs_vs_oracle(dev, na, nb, n, m, maker):
+    """All-pairs approximate EMD against the CPU restatement of approxmatch.cu + matchcost (tolerance: __expf vs expf,
+    summation order)."""
+    from oracle import cpu as ocpu
+    from pdgn_b200 import ops
+    rng = np.random.default_rng(na * 31 + n)
+    A, B = maker(rng, na, n, 3), maker(rng, nb, m, 3)
+    out = C(ops.emd_allpairs(G(A, dev), G(B, dev)))
+    x1, x2 = np.repeat(A, nb, axis=0), np.tile(B, (na, 1, 1))
+    ref = (ocpu.emd_cost(x1, x2) / np.float32(n)).reshape(na, nb)
+    np.testing.assert_allclose(out, ref, rtol=2e-4, atol=1e-7)
+
+
+def test_emd_against_recompiled_reference(dev):
+    """The reference's own ApproxMatch + MatchCost kernels (recompiled for sm_100a) on expanded pairs, as
+    _pairwise_EMD_CD_ calls them (evaluation_metrics.py:101-110)."""
+    rk = _ref()
+    from pdgn_b200 import evaluation_metrics as em
+    from pdgn_b200 import ops
+    rng = np.random.default_rng(41)
+    for n, maker in [(512, clouds_sphere), (2048, clouds_sphere), (1024, clouds_uniform)]:
+        A, B = G(maker(rng, 3, n, 3), dev), G(maker(rng, 4, n, 3), dev)
+        ours = ops.emd_allpairs(A, B)
+        for s_ in range(3):
+            rep = A[s_].view(1, -1, 3).expand(4, -1, -1).contiguous()
+            ref = rk.match_cost(rep, B) / float(n)
+            torch.testing.assert_close(ours[s_], ref, rtol=2e-4, atol=1e-7)
+        paired = em.emd_approx(A, B[:3].contiguous())
+        torch.testing.assert_close(paired, torch.diagonal(ours[:, :3]), rtol=1e-6, atol=0)
 
 
 # ------------------------------------------------------------------------------------------------ feature-space kNN
