@@ -52,11 +52,12 @@ extern "C" size_t pdgn_cd_allpairs_workspace(int na, int nb, int npts) {
 extern "C" int pdgn_cd_allpairs(const float* A, const float* B, int na, int nb, int npts, int row0, int row1, int col0,
                                 int col1, float* out, long long ld_out, void* workspace, size_t workspace_bytes,
                                 void* stream) {
-    if (!A || !B || !out || na < 0 || nb < 0 || npts <= 0) return PDGN_ERR_BAD_ARG;
+    if (na < 0 || nb < 0 || npts <= 0) return PDGN_ERR_BAD_ARG;
     if (row0 < 0 || row1 > na || row0 > row1 || col0 < 0 || col1 > nb || col0 > col1) return PDGN_ERR_BAD_ARG;
     if (npts > 16384) return PDGN_ERR_UNSUPPORTED;
     const int nrows = row1 - row0, ncols = col1 - col0;
-    if (nrows == 0 || ncols == 0) return PDGN_OK;
+    if (nrows == 0 || ncols == 0) return PDGN_OK;  // empty tile (pointers may be null)
+    if (!A || !B || !out) return PDGN_ERR_BAD_ARG;
     if (ld_out < ncols) return PDGN_ERR_BAD_ARG;
     const int npad = cd_npad(npts);
     const size_t need = ((size_t)nrows + ncols) * 3 * npad * sizeof(float);
@@ -83,8 +84,8 @@ extern "C" int pdgn_cd_allpairs(const float* A, const float* B, int na, int nb, 
     PDGN_CUDA(cudaFuncSetAttribute(PDGN_CD_KERNEL, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     const int spairs = (nrows + CD_NH - 1) / CD_NH;
     if (spairs > 65535) return PDGN_ERR_UNSUPPORTED;
-    // enough CTAs for >= ~20 waves of 2 CTAs/SM so the tail is small; each CTA walks `rstrip` B clouds
-    const int target = (sym ? 40 : 20) * CD_MINB * cd_num_sms();  // sym: about half the CTAs exit immediately
+    // enough CTAs that the last partial wave is a small fraction of the run; each CTA walks `rstrip` B clouds
+    const int target = (sym ? 128 : 64) * CD_MINB * cd_num_sms();  // ~64 waves: tail <= ~1.5 %; sym: half the CTAs exit at once
     int strips = (target + spairs - 1) / spairs;
     if (strips > ncols) strips = ncols;
     if (strips < 1) strips = 1;

@@ -136,10 +136,11 @@ using namespace pdgn;
 
 extern "C" int pdgn_chamfer_min(const float* x, const float* y, int b, int nx, int ny, int d, float* min_xy, int* arg_xy,
                                 float* min_yx, int* arg_yx, void* stream) {
-    if (!x || !y || b < 0 || nx < 0 || ny < 0) return PDGN_ERR_BAD_ARG;
+    if (b < 0 || nx < 0 || ny < 0) return PDGN_ERR_BAD_ARG;
     if (d < 1 || d > CH_DMAX || b > 65535) return PDGN_ERR_UNSUPPORTED;
     if ((!min_xy && arg_xy) || (!min_yx && arg_yx)) return PDGN_ERR_BAD_ARG;
     if (b == 0) return PDGN_OK;
+    if (!x || !y) return (nx == 0 && ny == 0) ? PDGN_OK : PDGN_ERR_BAD_ARG;
     if ((nx == 0) != (ny == 0)) return PDGN_ERR_BAD_ARG;  // a minimum over an empty set is undefined
     if (nx == 0) return PDGN_OK;
     cudaStream_t st = (cudaStream_t)stream;

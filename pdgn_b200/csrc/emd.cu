@@ -158,11 +158,12 @@ using namespace pdgn;
 
 extern "C" int pdgn_emd_allpairs(const float* A, const float* B, int na, int nb, int n, int m, int row0, int row1, int col0,
                                  int col1, float* out, long long ld_out, void* stream) {
-    if (!A || !B || !out || na < 0 || nb < 0 || n <= 0 || m <= 0) return PDGN_ERR_BAD_ARG;
+    if (na < 0 || nb < 0 || n <= 0 || m <= 0) return PDGN_ERR_BAD_ARG;
     if (row0 < 0 || row1 > na || row0 > row1 || col0 < 0 || col1 > nb || col0 > col1) return PDGN_ERR_BAD_ARG;
     if (n > EM_MAX || m > EM_MAX) return PDGN_ERR_UNSUPPORTED;
     const int nrows = row1 - row0, ncols = col1 - col0;
-    if (nrows == 0 || ncols == 0) return PDGN_OK;
+    if (nrows == 0 || ncols == 0) return PDGN_OK;  // empty tile (pointers may be null)
+    if (!A || !B || !out) return PDGN_ERR_BAD_ARG;
     if (ld_out < ncols || nrows > 65535) return ld_out < ncols ? PDGN_ERR_BAD_ARG : PDGN_ERR_UNSUPPORTED;
     const size_t smem = (size_t)2 * EM_MAX * sizeof(float4);
     PDGN_CUDA(cudaFuncSetAttribute(emd_allpairs_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));

@@ -685,9 +685,10 @@ using namespace pdgn;
     if (!(__VA_ARGS__)) return PDGN_ERR_BAD_ARG
 
 extern "C" int pdgn_group_fwd(const float* points, const int* idx, int b, int c, int n, int m, int k, float* out, void* stream) {
-    PDGN_GATHER_ARGS_OK(points && idx && out && b >= 0 && c >= 0 && n > 0 && m >= 0 && k >= 0);
+    PDGN_GATHER_ARGS_OK(b >= 0 && c >= 0 && n >= 0 && m >= 0 && k >= 0);
     const long long mk = (long long)m * k;
-    if (b == 0 || c == 0 || mk == 0) return PDGN_OK;
+    if (b == 0 || c == 0 || mk == 0) return PDGN_OK;  // empty output
+    PDGN_GATHER_ARGS_OK(points && idx && out && n > 0);
     if (mk > 0x7fffffffLL || b > 65535) return PDGN_ERR_UNSUPPORTED;
     const bool vec = (mk % 4 == 0) && ((reinterpret_cast<uintptr_t>(out) | reinterpret_cast<uintptr_t>(idx)) % 16 == 0);
     if (vec && c >= 8 && (size_t)n * 4 * 4 <= GS_ROW_BYTES) {
@@ -730,9 +731,10 @@ extern "C" size_t pdgn_group_bwd_workspace(int b, int n, int m, int k) {
 
 extern "C" int pdgn_group_bwd_ws(const float* grad_out, const int* idx, int b, int c, int n, int m, int k, float* grad_points,
                                  void* workspace, size_t workspace_bytes, void* stream) {
-    PDGN_GATHER_ARGS_OK(grad_out && idx && grad_points && b >= 0 && c >= 0 && n > 0 && m >= 0 && k >= 0);
+    PDGN_GATHER_ARGS_OK(b >= 0 && c >= 0 && n >= 0 && m >= 0 && k >= 0);
     const long long mk = (long long)m * k;
-    if (b == 0 || c == 0 || mk == 0) return PDGN_OK;
+    if (b == 0 || c == 0 || mk == 0) return PDGN_OK;  // nothing to add
+    PDGN_GATHER_ARGS_OK(grad_out && idx && grad_points && n > 0);
     if (mk > 0x7fffffffLL || b > 65535) return PDGN_ERR_UNSUPPORTED;
     const size_t row_bytes = (size_t)mk * 4;
     const size_t csr_smem = ((size_t)2 * n + 32) * sizeof(int);
@@ -760,9 +762,10 @@ extern "C" int pdgn_group_bwd_ws(const float* grad_out, const int* idx, int b, i
 
 extern "C" int pdgn_group_bwd(const float* grad_out, const int* idx, int b, int c, int n, int m, int k, float* grad_points,
                               void* stream) {
-    PDGN_GATHER_ARGS_OK(grad_out && idx && grad_points && b >= 0 && c >= 0 && n > 0 && m >= 0 && k >= 0);
+    PDGN_GATHER_ARGS_OK(b >= 0 && c >= 0 && n >= 0 && m >= 0 && k >= 0);
     const long long mk = (long long)m * k;
-    if (b == 0 || c == 0 || mk == 0) return PDGN_OK;
+    if (b == 0 || c == 0 || mk == 0) return PDGN_OK;  // nothing to add
+    PDGN_GATHER_ARGS_OK(grad_out && idx && grad_points && n > 0);
     if (mk > 0x7fffffffLL || b > 65535) return PDGN_ERR_UNSUPPORTED;
     const bool vec = (mk % 4 == 0) && ((reinterpret_cast<uintptr_t>(grad_out) | reinterpret_cast<uintptr_t>(idx)) % 16 == 0);
     const long long per = vec ? 4 : 1;
@@ -778,8 +781,9 @@ extern "C" int pdgn_group_bwd(const float* grad_out, const int* idx, int b, int 
 
 extern "C" int pdgn_interp_fwd(const float* points, const int* idx, const float* weight, int b, int c, int m, int n, float* out,
                                void* stream) {
-    PDGN_GATHER_ARGS_OK(points && idx && weight && out && b >= 0 && c >= 0 && m > 0 && n >= 0);
+    PDGN_GATHER_ARGS_OK(b >= 0 && c >= 0 && m >= 0 && n >= 0);
     if (b == 0 || c == 0 || n == 0) return PDGN_OK;
+    PDGN_GATHER_ARGS_OK(points && idx && weight && out && m > 0);
     if (b > 65535) return PDGN_ERR_UNSUPPORTED;
     const bool vec = (n % 4 == 0) && ((reinterpret_cast<uintptr_t>(out) | reinterpret_cast<uintptr_t>(idx) |
                                        reinterpret_cast<uintptr_t>(weight)) % 16 == 0);
@@ -820,8 +824,9 @@ extern "C" size_t pdgn_interp_bwd_workspace(int b, int n, int m) {
 
 extern "C" int pdgn_interp_bwd_ws(const float* grad_out, const int* idx, const float* weight, int b, int c, int n, int m,
                                   float* grad_points, void* workspace, size_t workspace_bytes, void* stream) {
-    PDGN_GATHER_ARGS_OK(grad_out && idx && weight && grad_points && b >= 0 && c >= 0 && m > 0 && n >= 0);
+    PDGN_GATHER_ARGS_OK(b >= 0 && c >= 0 && m >= 0 && n >= 0);
     if (b == 0 || c == 0 || n == 0) return PDGN_OK;
+    PDGN_GATHER_ARGS_OK(grad_out && idx && weight && grad_points && m > 0);
     if (b > 65535) return PDGN_ERR_UNSUPPORTED;
     const size_t csr_smem = ((size_t)2 * m + 32) * sizeof(int);
     int cc = PULL_CC;
@@ -845,8 +850,9 @@ extern "C" int pdgn_interp_bwd_ws(const float* grad_out, const int* idx, const f
 
 extern "C" int pdgn_interp_bwd(const float* grad_out, const int* idx, const float* weight, int b, int c, int n, int m,
                                float* grad_points, void* stream) {
-    PDGN_GATHER_ARGS_OK(grad_out && idx && weight && grad_points && b >= 0 && c >= 0 && m > 0 && n >= 0);
+    PDGN_GATHER_ARGS_OK(b >= 0 && c >= 0 && m >= 0 && n >= 0);
     if (b == 0 || c == 0 || n == 0) return PDGN_OK;
+    PDGN_GATHER_ARGS_OK(grad_out && idx && weight && grad_points && m > 0);
     if (b > 65535) return PDGN_ERR_UNSUPPORTED;
     const unsigned gx = (unsigned)((n + GT - 1) / GT);
     const int cpb = pick_cpb((long long)gx * b, c);
@@ -858,9 +864,10 @@ extern "C" int pdgn_interp_bwd(const float* grad_out, const int* idx, const floa
 }
 
 extern "C" int pdgn_edge_feat_fwd(const float* x, const int64_t* idx, int b, int c, int n, int k, float* ee, void* stream) {
-    PDGN_GATHER_ARGS_OK(x && idx && ee && b >= 0 && c >= 0 && n >= 0 && k >= 0);
+    PDGN_GATHER_ARGS_OK(b >= 0 && c >= 0 && n >= 0 && k >= 0);
     const long long nk = (long long)n * k;
     if (b == 0 || c == 0 || nk == 0) return PDGN_OK;
+    PDGN_GATHER_ARGS_OK(x && idx && ee);
     if (b > 65535 || nk > 0x7fffffffLL) return PDGN_ERR_UNSUPPORTED;
     const bool vec = (nk % 4 == 0) && (reinterpret_cast<uintptr_t>(ee) % 16 == 0);
     const long long per = vec ? 4 : 1;
@@ -877,8 +884,9 @@ extern "C" int pdgn_edge_feat_fwd(const float* x, const int64_t* idx, int b, int
 
 extern "C" int pdgn_edge_feat_bwd(const float* grad_ee, const int64_t* idx, int b, int c, int n, int k, float* grad_x,
                                   void* stream) {
-    PDGN_GATHER_ARGS_OK(grad_ee && idx && grad_x && b >= 0 && c >= 0 && n >= 0 && k >= 0);
+    PDGN_GATHER_ARGS_OK(b >= 0 && c >= 0 && n >= 0 && k >= 0);
     if (b == 0 || c == 0 || n == 0 || k == 0) return PDGN_OK;
+    PDGN_GATHER_ARGS_OK(grad_ee && idx && grad_x);
     if (b > 65535) return PDGN_ERR_UNSUPPORTED;
     const unsigned gx = (unsigned)((n + GT - 1) / GT);
     const int cpb = pick_cpb((long long)gx * b, c);
@@ -896,8 +904,9 @@ extern "C" size_t pdgn_edge_feat_bwd_workspace(int b, int n, int k) {
 
 extern "C" int pdgn_edge_feat_bwd_ws(const float* grad_ee, const int64_t* idx, int b, int c, int n, int k, float* grad_x,
                                      void* workspace, size_t workspace_bytes, void* stream) {
-    PDGN_GATHER_ARGS_OK(grad_ee && idx && grad_x && b >= 0 && c >= 0 && n >= 0 && k >= 0);
+    PDGN_GATHER_ARGS_OK(b >= 0 && c >= 0 && n >= 0 && k >= 0);
     if (b == 0 || c == 0 || n == 0 || k == 0) return PDGN_OK;
+    PDGN_GATHER_ARGS_OK(grad_ee && idx && grad_x);
     if (b > 65535) return PDGN_ERR_UNSUPPORTED;
     const long long nk = (long long)n * k;
     const size_t csr_smem = ((size_t)2 * n + 32) * sizeof(int);

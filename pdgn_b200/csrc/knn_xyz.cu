@@ -366,16 +366,18 @@ static int knn_dispatch(const float* xyz, const float* new_xyz, int b, int n, in
 using namespace pdgn;
 
 extern "C" int pdgn_knn_xyz(const float* xyz, const float* new_xyz, int b, int n, int m, int k, int* idx, float* dist2, void* stream) {
-    if (!xyz || !new_xyz || !idx || b < 0 || n < 0 || m < 0 || k < 1) return PDGN_ERR_BAD_ARG;
+    if (b < 0 || n < 0 || m < 0 || k < 1) return PDGN_ERR_BAD_ARG;
     if (k > 128 || b > 65535) return PDGN_ERR_UNSUPPORTED;
-    if (b == 0 || m == 0) return PDGN_OK;
+    if (b == 0 || m == 0) return PDGN_OK;  // empty query set: nothing to write (pointers may be null)
+    if (!new_xyz || !idx || (!xyz && n > 0)) return PDGN_ERR_BAD_ARG;
     // n == 0 falls through to the generic kernel, which leaves the reference's initial values (idx 0, dist +inf)
     return knn_dispatch(xyz, new_xyz, b, n, m, k, idx, dist2, (cudaStream_t)stream);
 }
 
 extern "C" int pdgn_nn3(const float* unknown, const float* known, int b, int n, int m, float* dist2, int* idx, void* stream) {
-    if (!unknown || !known || !dist2 || !idx || b < 0 || n < 0 || m <= 0) return PDGN_ERR_BAD_ARG;
+    if (b < 0 || n < 0 || m < 0) return PDGN_ERR_BAD_ARG;
     if (b > 65535) return PDGN_ERR_UNSUPPORTED;
     if (b == 0 || n == 0) return PDGN_OK;
+    if (!unknown || !dist2 || !idx || (!known && m > 0)) return PDGN_ERR_BAD_ARG;
     return knn_dispatch(known, unknown, b, m, n, 3, idx, dist2, (cudaStream_t)stream);
 }

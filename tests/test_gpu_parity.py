@@ -448,3 +448,58 @@ def test_streams_and_errors(dev):
         ops.knn_xyz(500, xyz)
     with pytest.raises(PdgnError):
         ops.knn_feat(torch.zeros(1, 4, 8, device=dev), 10)
+
+
+# ------------------------------------------------------------------------------------------------ edge cases
+def test_empty_and_degenerate_inputs(dev):
+    """Zero-sized batches / query sets / neighbour lists: no launch, correctly shaped empty outputs, no crash."""
+    from pdgn_b200 import ops, pointops
+    z = lambda *s, dt=torch.float32: torch.zeros(*s, dtype=dt, device=dev)
+    assert tuple(ops.knn_xyz(4, z(0, 16, 3)).shape) == (0, 16, 4)
+    assert tuple(ops.knn_xyz(4, z(2, 16, 3), z(2, 0, 3)).shape) == (2, 0, 4)
+    idx, d2 = ops.knn_xyz(3, z(2, 0, 3), z(2, 5, 3), return_dist=True)      # nothing to select from
+    assert torch.all(idx == 0) and torch.all(torch.isinf(d2))
+    assert tuple(ops.group_fwd(z(2, 0, 9), z(2, 4, 3, dt=torch.int32)).shape) == (2, 0, 4, 3)
+    assert tuple(ops.group_fwd(z(2, 5, 9), z(2, 0, 3, dt=torch.int32)).shape) == (2, 5, 0, 3)
+    assert torch.all(ops.group_bwd(z(2, 5, 0, 3), z(2, 0, 3, dt=torch.int32), 9) == 0)
+    assert tuple(ops.interp_fwd(z(0, 4, 8), z(0, 6, 3, dt=torch.int32), z(0, 6, 3)).shape) == (0, 4, 6)
+    assert tuple(ops.cd_allpairs(z(0, 64, 3), z(3, 64, 3)).shape) == (0, 3)
+    assert tuple(ops.cd_allpairs(z(3, 64, 3), z(0, 64, 3)).shape) == (3, 0)
+    assert tuple(ops.emd_allpairs(z(0, 64, 3), z(3, 64, 3)).shape) == (0, 3)
+    m = ops.chamfer_min(z(0, 5, 3), z(0, 7, 3))
+    assert tuple(m[0].shape) == (0, 5) and tuple(m[2].shape) == (0, 7)
+    one = torch.rand(1, 1, 3, device=dev)                                   # a single point against itself
+    assert ops.knn_xyz(1, one).item() == 0
+    assert ops.cd_allpairs(one, one).item() == 0.0
+    g = pointops.Gen_QueryAndGroupXYZ(nsample=2)(torch.rand(1, 2, 3, device=dev))
+    assert tuple(g.shape) == (1, 3, 2, 2)
+
+
+def test_large_clouds_cfg5_shapes(dev):
+    """BASELINE config 5 shapes at reduced batch: 16384-point clouds, kNN k=32, and CD between 16384-point clouds."""
+    from oracle import cpu as ocpu
+    from pdgn_b200 import ops
+    rng = np.random.default_rng(50)
+    xyz = clouds_sphere(rng, 2, 16384, 3)
+    q = xyz[:, :777].copy()
+    idx, d2 = ops.knn_xyz(32, G(xyz, dev), G(q, dev), return_dist=True)
+    ridx, rd2 = ocpu.knn_xyz(xyz, q, 32)
+    np.testing.assert_array_equal(C(idx), ridx)
+    np.testing.assert_array_equal(C(d2), rd2)
+    A, B = clouds_sphere(rng, 2, 16384, 3), clouds_sphere(rng, 1, 16384, 3)
+    np.testing.assert_allclose(C(ops.cd_allpairs(G(A, dev), G(B, dev))), ocpu.cd_allpairs(A, B), rtol=3e-6)
+
+
+def test_results_do_not_depend_on_launch_geometry(dev):
+    """The same cloud pair must give the same CD scalar whatever tile / strip it lands in (2-D tiling, rank grids)."""
+    from pdgn_b200 import ops
+    rng = np.random.default_rng(51)
+    A, B = G(clouds_sphere(rng, 37, 512, 3), dev), G(clouds_sphere(rng, 29, 512, 3), dev)
+    full = ops.cd_allpairs(A, B)
+    from pdgn_b200 import dist as pd
+    for world in (2, 4, 8):
+        out = torch.empty_like(full)
+        for r in range(world):
+            rows, cols = pd.tile_of(r, world, 37, 29)
+            out[rows[0]:rows[1], cols[0]:cols[1]] = ops.cd_allpairs(A, B, rows=rows, cols=cols)
+        assert torch.equal(out, full)
