@@ -76,6 +76,100 @@ __global__ void __launch_bounds__(KG_T) knn_generic_kernel(const float* __restri
 }
 
 // =====================================================================================================
+// small-k kernel (k <= 4: the 3-NN of nearestneighbor): register-resident sorted list per query
+// =====================================================================================================
+// With k this small a record-breaking candidate is rare (k + k ln(n/k) per query), so the classic scan is efficient:
+// 6 FMA-pipe instructions + one compare per pair, and a short branch when some lane of the warp improves its list.
+constexpr int KK_T = 128;
+constexpr int KK_R = 2;      // queries per thread
+constexpr int KK_TILE = 2048;
+
+template <int K>
+__global__ void __launch_bounds__(KK_T) knn_smallk_kernel(const float* __restrict__ xyz, const float* __restrict__ new_xyz, int n,
+                                                         int m, int* __restrict__ idx, float* __restrict__ dist2) {
+    __shared__ __align__(16) float tile[3 * KK_TILE];
+    const int bz = blockIdx.y, t = threadIdx.x;
+    const float* pb = xyz + (size_t)bz * n * 3;
+    float qx[KK_R], qy[KK_R], qz[KK_R], bd[KK_R][K];
+    int bi[KK_R][K];
+#pragma unroll
+    for (int r = 0; r < KK_R; ++r) {
+        const int q = min(blockIdx.x * (KK_T * KK_R) + r * KK_T + t, m - 1);
+        const float* qp = new_xyz + ((size_t)bz * m + q) * 3;
+        qx[r] = qp[0]; qy[r] = qp[1]; qz[r] = qp[2];
+#pragma unroll
+        for (int e = 0; e < K; ++e) { bd[r][e] = kInf; bi[r][e] = 0; }
+    }
+    for (int j0 = 0; j0 < n; j0 += KK_TILE) {
+        const int cnt = min(KK_TILE, n - j0);
+        __syncthreads();
+        for (int e = t; e < cnt * 3; e += KK_T) {
+            const int j = e / 3, c = e - j * 3;
+            tile[c * KK_TILE + j] = pb[(size_t)j0 * 3 + e];
+        }
+        if (t < ((cnt + 3) & ~3) - cnt) {  // NaN padding: never strictly smaller than anything
+            const float nanv = __int_as_float(0x7fc00000);
+            tile[cnt + t] = nanv; tile[KK_TILE + cnt + t] = nanv; tile[2 * KK_TILE + cnt + t] = nanv;
+        }
+        __syncthreads();
+#pragma unroll 2
+        for (int j = 0; j < cnt; j += 4) {
+            const float4 X = *reinterpret_cast<const float4*>(tile + j);
+            const float4 Y = *reinterpret_cast<const float4*>(tile + KK_TILE + j);
+            const float4 Z = *reinterpret_cast<const float4*>(tile + 2 * KK_TILE + j);
+#pragma unroll
+            for (int r = 0; r < KK_R; ++r) {
+                float d[4];
+                d[0] = d2_xyz(qx[r], qy[r], qz[r], X.x, Y.x, Z.x);
+                d[1] = d2_xyz(qx[r], qy[r], qz[r], X.y, Y.y, Z.y);
+                d[2] = d2_xyz(qx[r], qy[r], qz[r], X.z, Y.z, Z.z);
+                d[3] = d2_xyz(qx[r], qy[r], qz[r], X.w, Y.w, Z.w);
+                if (min3(fminf(d[0], d[1]), d[2], d[3]) < bd[r][K - 1]) {  // rare: some candidate of the quad enters the list
+#pragma unroll
+                    for (int u = 0; u < 4; ++u) {
+                        if (d[u] < bd[r][K - 1]) {
+                            float dv = d[u];
+                            int iv = j0 + j + u;
+                            bool shifting = false;  // once inserted, the displaced entries shift down unconditionally
+#pragma unroll
+                            for (int e = 0; e < K; ++e) {  // strict '<': equal distances keep the lower index first
+                                if (shifting || dv < bd[r][e]) {
+                                    shifting = true;
+                                    const float td = bd[r][e];
+                                    const int ti = bi[r][e];
+                                    bd[r][e] = dv; bi[r][e] = iv;
+                                    dv = td; iv = ti;
+                                }
+                            }
+                        }
+                    }
+                }
+            }
+        }
+    }
+#pragma unroll
+    for (int r = 0; r < KK_R; ++r) {
+        const int q = blockIdx.x * (KK_T * KK_R) + r * KK_T + t;
+        if (q < m) {
+            const size_t o = ((size_t)bz * m + q) * K;
+#pragma unroll
+            for (int e = 0; e < K; ++e) {
+                idx[o + e] = bi[r][e];
+                if (dist2) dist2[o + e] = bd[r][e];
+            }
+        }
+    }
+}
+
+template <int K>
+static int launch_smallk(const float* xyz, const float* new_xyz, int b, int n, int m, int* idx, float* dist2, cudaStream_t st) {
+    dim3 grid((m + KK_T * KK_R - 1) / (KK_T * KK_R), b);
+    knn_smallk_kernel<K><<<grid, KK_T, 0, st>>>(xyz, new_xyz, n, m, idx, dist2);
+    PDGN_CHECK_LAUNCH();
+    return PDGN_OK;
+}
+
+// =====================================================================================================
 // fast kernel: minima scan + warp-cooperative selection
 // =====================================================================================================
 constexpr int KS_TILE = 2048;   // candidate capacity of the shared tile
@@ -347,6 +441,13 @@ static bool select_plan(int n, int k, int G, int* log2ss, int* gsz) {
 
 static int knn_dispatch(const float* xyz, const float* new_xyz, int b, int n, int m, int k, int* idx, float* dist2, cudaStream_t st) {
     int log2ss = 0, gsz = 0;
+    switch (k) {  // tiny k: register-resident lists
+        case 1: return launch_smallk<1>(xyz, new_xyz, b, n, m, idx, dist2, st);
+        case 2: return launch_smallk<2>(xyz, new_xyz, b, n, m, idx, dist2, st);
+        case 3: return launch_smallk<3>(xyz, new_xyz, b, n, m, idx, dist2, st);
+        case 4: return launch_smallk<4>(xyz, new_xyz, b, n, m, idx, dist2, st);
+        default: break;
+    }
     // k <= 24 of 32 groups / k <= 48 of 64 groups keeps the expected survivor count (~G/(G-k) * k-ish) well under KS_SCAP
     if (k <= 24 && select_plan(n, k, 32, &log2ss, &gsz)) {
         if (m > 256) return launch_select<32, 16>(xyz, new_xyz, b, n, m, k, log2ss, gsz, idx, dist2, st);
