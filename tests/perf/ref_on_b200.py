@@ -1,6 +1,6 @@
 """'Reference on B200' column: time the reference's own CUDA kernels, recompiled unmodified for
-sm_100a (oracle/_ref), next to the pdgn_b200 kernels on the same shapes.  tools/ only -- not a product path.
-Usage (GPU box): python tools/ref_on_b200.py > gpurun_out/ref_on_b200.txt"""
+sm_100a (oracle/_ref), next to the pdgn_b200 kernels on the same shapes.  Lives under tests/ because it executes oracle/_ref (test infrastructure); not collected by pytest.
+Usage (GPU box): python tests/perf/ref_on_b200.py > gpurun_out/ref_on_b200.txt"""
 import os
 import sys
 import time
@@ -8,7 +8,7 @@ import time
 import numpy as np
 import torch
 
-sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__)))))
 from oracle import ref_kernels as rk  # noqa: E402
 from pdgn_b200 import ops  # noqa: E402
 
