@@ -26,7 +26,8 @@ constexpr int CD_NH = 2;      // halves (A clouds) per CTA
 constexpr int CD_MINB = 2;    // CTAs per SM the register allocation must allow
 constexpr int CD_VARIANT = CDV_PRED_RED | CDV_PREFETCH;  // +2.3 % over the plain loop (profiles/r01_cd_tune_*.txt)
 constexpr int CD_THREADS = CD_NH * CD_HALF;
-#define PDGN_CD_KERNEL cd_allpairs_kernel<CD_R, CD_NH, CD_MINB, CD_VARIANT>
+#define PDGN_CD_KERNEL cd_allpairs_kernel<CD_R, CD_NH, CD_MINB, CD_VARIANT, false>
+#define PDGN_CD_KERNEL_SYM cd_allpairs_kernel<CD_R, CD_NH, CD_MINB, CD_VARIANT, true>
 
 static int cd_num_sms() {
     static int sms = 0;
@@ -82,6 +83,7 @@ extern "C" int pdgn_cd_allpairs(const float* A, const float* B, int na, int nb, 
 
     const size_t smem = cd_smem_bytes<CD_NH, CD_VARIANT>(npad);
     PDGN_CUDA(cudaFuncSetAttribute(PDGN_CD_KERNEL, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    PDGN_CUDA(cudaFuncSetAttribute(PDGN_CD_KERNEL_SYM, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     const int spairs = (nrows + CD_NH - 1) / CD_NH;
     if (spairs > 65535) return PDGN_ERR_UNSUPPORTED;
     // enough CTAs that the last partial wave is a small fraction of the run; each CTA walks `rstrip` B clouds
@@ -91,7 +93,8 @@ extern "C" int pdgn_cd_allpairs(const float* A, const float* B, int na, int nb, 
     if (strips < 1) strips = 1;
     const int rstrip = (ncols + strips - 1) / strips;
     strips = (ncols + rstrip - 1) / rstrip;
-    PDGN_CD_KERNEL<<<dim3(strips, spairs), CD_THREADS, smem, st>>>(PA, PB, nrows, ncols, npts, npad, rstrip, sym ? 1 : 0, out, ld_out);
+    if (sym) PDGN_CD_KERNEL_SYM<<<dim3(strips, spairs), CD_THREADS, smem, st>>>(PA, PB, nrows, ncols, npts, npad, rstrip, out, ld_out);
+    else PDGN_CD_KERNEL<<<dim3(strips, spairs), CD_THREADS, smem, st>>>(PA, PB, nrows, ncols, npts, npad, rstrip, out, ld_out);
     PDGN_CHECK_LAUNCH();
     if (sym) {
         cd_mirror_kernel<<<dim3((nrows + 31) / 32, (nrows + 7) / 8), dim3(32, 8), 0, st>>>(out, nrows, ld_out);

@@ -105,10 +105,10 @@ __device__ __forceinline__ void cd_two_candidates_aos(const float (&qx)[R], cons
 }
 
 // NH halves of 128 threads per CTA; each half owns one A cloud (R rows per thread, CD_ROWS = R*128 per row block).
-template <int R, int NH, int MINB, int VAR>
+template <int R, int NH, int MINB, int VAR, bool SYM = false>
 __global__ void __launch_bounds__(NH * CD_HALF, MINB)
 cd_allpairs_kernel(const float* __restrict__ PA, const float* __restrict__ PB, int nrows, int ncols, int npts, int npad,
-                   int rstrip, int sym, float* __restrict__ out, long long ld_out) {
+                   int rstrip, float* __restrict__ out, long long ld_out) {
     constexpr int ROWS = R * CD_HALF;
     extern __shared__ __align__(128) unsigned char smem_raw[];
     constexpr int STAGE = ((VAR & CDV_AOS) ? 4 : 3) * CD_TILE;                // floats per stage
@@ -121,11 +121,11 @@ cd_allpairs_kernel(const float* __restrict__ PA, const float* __restrict__ PB, i
     int s = blockIdx.y * NH + half;
     const bool s_valid = s < nrows;
     if (!s_valid) s = nrows - 1;  // ragged row count: spare halves recompute the last cloud and discard it
-    // sym: A and B are the same cloud set => CD(s,r) == CD(r,s); this CTA only walks r >= its first row, the lower
+    // SYM: A and B are the same cloud set => CD(s,r) == CD(r,s); this CTA only walks r >= its first row, the lower
     // triangle is filled by cd_mirror_kernel afterwards (saves ~half the work of the rr / ss matrices)
-    const int r_begin = sym ? max((int)(blockIdx.x * rstrip), (int)(blockIdx.y * NH)) : blockIdx.x * rstrip;
+    const int r_begin = SYM ? max((int)(blockIdx.x * rstrip), (int)(blockIdx.y * NH)) : blockIdx.x * rstrip;
     const int r_end = min(ncols, (int)(blockIdx.x * rstrip) + rstrip);
-    if (r_begin >= r_end) return;
+    if (SYM && r_begin >= r_end) return;
     const int nrb = (npts + ROWS - 1) / ROWS;
     const int ncb = (npad + CD_TILE - 1) / CD_TILE;
     const int ntiles = (r_end - r_begin) * nrb * ncb;

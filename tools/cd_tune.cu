@@ -25,13 +25,13 @@ float run(const char* name, const float* PA, const float* PB_soa, const float* P
     int strips = (target + spairs - 1) / spairs; if (strips > n) strips = n; if (strips < 1) strips = 1;
     const int rstrip = (n + strips - 1) / strips; strips = (n + rstrip - 1) / rstrip;
     CK(cudaMemset(out, 0, sizeof(float) * n * n));
-    kern<<<dim3(strips, spairs), NH * CD_HALF, smem>>>(PA, PB, n, n, npts, npad, rstrip, 0, out, n);
+    kern<<<dim3(strips, spairs), NH * CD_HALF, smem>>>(PA, PB, n, n, npts, npad, rstrip, out, n);
     CK(cudaDeviceSynchronize());
     cudaEvent_t e0, e1; cudaEventCreate(&e0); cudaEventCreate(&e1);
     float best = 1e30f;
     for (int it = 0; it < 3; ++it) {
         CK(cudaEventRecord(e0));
-        kern<<<dim3(strips, spairs), NH * CD_HALF, smem>>>(PA, PB, n, n, npts, npad, rstrip, 0, out, n);
+        kern<<<dim3(strips, spairs), NH * CD_HALF, smem>>>(PA, PB, n, n, npts, npad, rstrip, out, n);
         CK(cudaEventRecord(e1)); CK(cudaDeviceSynchronize());
         float ms; cudaEventElapsedTime(&ms, e0, e1); if (ms < best) best = ms;
     }
