@@ -31,8 +31,8 @@ __device__ __forceinline__ float sqrt_fast(float x) {
     return r;
 }
 
-constexpr int EM_T = 256;             // threads per CTA
-constexpr int EM_R = 8;               // points of each cloud owned per thread
+constexpr int EM_T = 512;             // threads per CTA
+constexpr int EM_R = 4;               // points of each cloud owned per thread (8 warps/SMSP keep the MUFU queue fed)
 constexpr int EM_MAX = EM_T * EM_R;   // 2048 points per cloud
 
 __global__ void __launch_bounds__(EM_T, 2)

@@ -109,7 +109,7 @@ def test_nn3_bit_exact(dev):
 
 # ------------------------------------------------------------------------------------------------ gathers
 @pytest.mark.parametrize("b,c,n,m,k", [(2, 3, 2048, 2048, 20), (3, 5, 100, 37, 7), (2, 64, 256, 256, 10), (1, 1, 9, 1, 1),
-                                       (2, 33, 128, 50, 3)])
+                                       (2, 33, 128, 50, 3), (2, 8, 1500, 700, 6), (1, 6, 40, 3000, 4), (1, 20, 5000, 64, 4)])
 def test_grouping_fwd_bit_exact_bwd_close(dev, b, c, n, m, k):
     from oracle import cpu as ocpu
     from pdgn_b200 import pointops
@@ -124,7 +124,8 @@ def test_grouping_fwd_bit_exact_bwd_close(dev, b, c, n, m, k):
     np.testing.assert_allclose(C(f.grad), ocpu.group_bwd(go, idx, n), rtol=1e-5, atol=1e-5)
 
 
-@pytest.mark.parametrize("b,c,m,n", [(2, 64, 1024, 2048), (3, 5, 17, 33), (1, 256, 128, 256), (2, 7, 40, 10)])
+@pytest.mark.parametrize("b,c,m,n", [(2, 64, 1024, 2048), (3, 5, 17, 33), (1, 256, 128, 256), (2, 7, 40, 10), (1, 9, 3, 4000),
+                                     (2, 12, 2500, 300)])
 def test_interpolation_fwd_bit_exact_bwd_close(dev, b, c, m, n):
     from oracle import cpu as ocpu
     from pdgn_b200 import pointops
@@ -340,7 +341,7 @@ def test_emd_against_recompiled_reference(dev):
 
 # ------------------------------------------------------------------------------------------------ feature-space kNN
 @pytest.mark.parametrize("b,c,n,k", [(2, 16, 64, 10), (3, 32, 128, 10), (2, 64, 256, 10), (1, 128, 512, 10), (2, 7, 100, 5),
-                                     (1, 256, 1024, 10)])
+                                     (1, 256, 1024, 10), (1, 12, 1300, 4), (2, 5, 333, 3)])
 def test_knn_feat_bit_exact_and_edge_features(dev, b, c, n, k):
     from oracle import cpu as ocpu
     from oracle import torch_ref as tref
