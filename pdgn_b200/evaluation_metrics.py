@@ -15,6 +15,7 @@ are omitted.
 import os
 import warnings
 
+import numpy as np
 import torch
 
 from . import ops
@@ -139,3 +140,107 @@ def compute_all_metrics(sample_pcs, ref_pcs, batch_size=None, accelerated_cd=Fal
     else:
         warnings.warn("pdgn_b200: PDGN_B200_SKIP_EMD is set; only the -CD keys are returned", stacklevel=2)
     return results
+
+
+#######################################################
+# JSD (evaluation_metrics.py:206-321) -- next row 8f-4
+#######################################################
+def unit_cube_grid_point_cloud(resolution, clip_sphere=False):
+    """evaluation_metrics.py:206-224: centres of a resolution^3 grid in the unit cube (numpy, as the reference returns)."""
+    spacing = 1.0 / float(resolution - 1)
+    ax = (np.arange(resolution, dtype=np.float32) * np.float32(spacing) - np.float32(0.5)).astype(np.float32)
+    grid = np.stack(np.meshgrid(ax, ax, ax, indexing="ij"), axis=-1).astype(np.float32)
+    if clip_sphere:
+        grid = grid.reshape(-1, 3)
+        grid = grid[np.linalg.norm(grid, axis=1) <= 0.5]
+    return grid, spacing
+
+
+def _nearest_grid_index(points, resolution, in_sphere):
+    """Index (into the possibly sphere-clipped grid list) of the nearest grid centre for every point [P,3] on the GPU.
+    The nearest centre of the FULL regular grid is a rounding; it is also the nearest ALLOWED centre whenever it lies inside
+    the sphere (true for all but a handful of boundary points), and those few go through the exact 1-NN kernel."""
+    dev = points.device
+    spacing = 1.0 / float(resolution - 1)
+    cell = torch.clamp(torch.round((points + 0.5) / spacing), 0, resolution - 1).long()
+    flat = (cell[:, 0] * resolution + cell[:, 1]) * resolution + cell[:, 2]
+    if not in_sphere:
+        return flat, resolution ** 3
+    grid_np, _ = unit_cube_grid_point_cloud(resolution, True)
+    full_np, _ = unit_cube_grid_point_cloud(resolution, False)
+    keep = np.linalg.norm(full_np.reshape(-1, 3), axis=1) <= 0.5
+    lut = torch.full((resolution ** 3,), -1, dtype=torch.long, device=dev)
+    lut[torch.from_numpy(np.nonzero(keep)[0]).to(dev)] = torch.arange(int(keep.sum()), device=dev)
+    out = lut[flat]
+    miss = out < 0
+    if bool(miss.any()):
+        grid = torch.from_numpy(grid_np).to(dev).unsqueeze(0).contiguous()
+        q = points[miss].unsqueeze(0).contiguous()
+        out[miss] = ops.knn_xyz(1, grid, q).view(-1).long()
+    return out, int(keep.sum())
+
+
+def entropy_of_occupancy_grid(pclouds, grid_resolution, in_sphere=False, verbose=False):
+    """evaluation_metrics.py:241-280 on the GPU: (mean cell entropy, per-cell point counters [numpy float64])."""
+    pcs = torch.as_tensor(pclouds, dtype=torch.float32)
+    if not pcs.is_cuda:
+        pcs = pcs.cuda()
+    n_clouds, n_pts, _ = pcs.shape
+    epsilon = 10e-4
+    bound = 0.5 + epsilon
+    if verbose and (abs(pcs.max().item()) > bound or abs(pcs.min().item()) > bound):
+        warnings.warn("Point-clouds are not in unit cube.")
+    if verbose and in_sphere and pcs.pow(2).sum(dim=2).sqrt().max().item() > bound:
+        warnings.warn("Point-clouds are not in unit sphere.")
+    idx, n_cells = _nearest_grid_index(pcs.reshape(-1, 3).contiguous(), grid_resolution, in_sphere)
+    counters = torch.bincount(idx, minlength=n_cells).double()
+    cloud_id = torch.arange(n_clouds, device=pcs.device).repeat_interleave(n_pts)
+    per_cloud = torch.unique(cloud_id * n_cells + idx)
+    bern = torch.bincount(per_cloud % n_cells, minlength=n_cells).double()
+    p = bern[bern > 0] / float(n_clouds)
+    q = 1.0 - p
+    ent = -(p * torch.log(p)) - torch.where(q > 0, q * torch.log(torch.clamp(q, min=1e-300)), torch.zeros_like(q))
+    return float(ent.sum().item()) / float(n_cells), counters.cpu().numpy()
+
+
+def jensen_shannon_divergence(P, Q):
+    """evaluation_metrics.py:283-302 (base-2 entropies; tiny vectors, host side)."""
+    P = np.asarray(P, dtype=np.float64)
+    Q = np.asarray(Q, dtype=np.float64)
+    if np.any(P < 0) or np.any(Q < 0):
+        raise ValueError("Negative values.")
+    if len(P) != len(Q):
+        raise ValueError("Non equal size.")
+    P_ = P / np.sum(P)
+    Q_ = Q / np.sum(Q)
+
+    def _entropy2(v):
+        v = v[v > 0]
+        return float(-(v * np.log2(v)).sum())
+
+    res = _entropy2((P_ + Q_) / 2.0) - (_entropy2(P_) + _entropy2(Q_)) / 2.0
+    res2 = _jsdiv(P_, Q_)
+    if not np.allclose(res, res2, atol=10e-5, rtol=0):
+        warnings.warn("Numerical values of two JSD methods don't agree.")
+    return res
+
+
+def _jsdiv(P, Q):
+    """evaluation_metrics.py:305-321."""
+    def _kldiv(A, B):
+        idx = np.logical_and(A > 0, B > 0)
+        a, b = A[idx], B[idx]
+        return float(np.sum(a * np.log2(a / b)))
+
+    P_ = P / np.sum(P)
+    Q_ = Q / np.sum(Q)
+    M = 0.5 * (P_ + Q_)
+    return 0.5 * (_kldiv(P_, M) + _kldiv(Q_, M))
+
+
+def jsd_between_point_cloud_sets(sample_pcs, ref_pcs, resolution=28):
+    """evaluation_metrics.py:227-238: JSD between the occupancy-grid distributions of two cloud sets (numpy or torch in)."""
+    in_unit_sphere = True
+    sample_grid_var = entropy_of_occupancy_grid(sample_pcs, resolution, in_unit_sphere)[1]
+    ref_grid_var = entropy_of_occupancy_grid(ref_pcs, resolution, in_unit_sphere)[1]
+    return jensen_shannon_divergence(sample_grid_var, ref_grid_var)

@@ -90,6 +90,22 @@ def main():
         ev["mmdcov:" + k] = np.asarray(v.item(), dtype=np.float64)
     for k, v in nn1.items():
         ev["knn:" + k] = np.asarray(v.item(), dtype=np.float64)
+    # JSD (evaluation_metrics.py:206-321): numpy + sklearn + scipy on the reference side
+    from numpy.linalg import norm
+    from scipy.stats import entropy
+    from sklearn.neighbors import NearestNeighbors
+    import warnings
+    ns3 = {"np": np, "norm": norm, "entropy": entropy, "NearestNeighbors": NearestNeighbors, "warnings": warnings}
+    extract(os.path.join(REF, "evaluation/evaluation_metrics.py"),
+            ["unit_cube_grid_point_cloud", "jsd_between_point_cloud_sets", "entropy_of_occupancy_grid",
+             "jensen_shannon_divergence", "_jsdiv"], ns3)
+    jsmp = (clouds(g, 12, 512, 3, kind="S") * 0.5).numpy()      # inside the radius-0.5 sphere the grid is clipped to
+    jref = (clouds(g, 10, 512, 3, kind="U") * 0.28).numpy()
+    ent_s, cnt_s = ns3["entropy_of_occupancy_grid"](jsmp, 28, True)
+    ent_r, cnt_r = ns3["entropy_of_occupancy_grid"](jref, 28, True)
+    ev.update({"jsd_smp": jsmp, "jsd_ref": jref, "jsd_value": np.asarray(ns3["jsd_between_point_cloud_sets"](jsmp, jref), dtype=np.float64),
+               "jsd_entropy_smp": np.asarray(ent_s, dtype=np.float64), "jsd_entropy_ref": np.asarray(ent_r, dtype=np.float64),
+               "jsd_counters_smp": cnt_s, "jsd_counters_ref": cnt_r})
     np.savez_compressed(os.path.join(OUT, "evaluation_metrics.npz"), **ev)
 
     # ---- get_edge_features{,_xyz} (models/PDGNet_v2.py:439-528) -------------------------------------

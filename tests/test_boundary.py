@@ -98,7 +98,9 @@ def test_modules_mirror_the_reference_names(built):
                  "Interpolation", "Gen_QueryAndGroupXYZ", "QueryAndGroup", "GroupAll", "knnquery_naive", "knnquery_exclude"]:
         assert hasattr(pointops, name), name
     assert hasattr(chamfer_loss, "ChamferLoss")
-    for name in ["distChamfer", "distChamferCUDA", "EMD_CD", "_pairwise_EMD_CD_", "knn", "lgan_mmd_cov", "compute_all_metrics"]:
+    for name in ["distChamfer", "distChamferCUDA", "emd_approx", "EMD_CD", "_pairwise_EMD_CD_", "knn", "lgan_mmd_cov",
+                 "compute_all_metrics", "unit_cube_grid_point_cloud", "jsd_between_point_cloud_sets", "entropy_of_occupancy_grid",
+                 "jensen_shannon_divergence"]:  # every def of the reference's evaluation_metrics.py
         assert hasattr(evaluation_metrics, name), name
     for name in ["get_edge_features", "get_edge_features_xyz"]:
         assert hasattr(edge_features, name), name
