@@ -10,6 +10,7 @@
 // output positions (one 16-byte streaming store per channel), reads its 4 indices ONCE and walks the
 // channels of its chunk, so idx is read once per channel chunk instead of once per channel (the reference
 // re-reads it C times) and the random 4-byte gathers hit L1/L2-resident feature rows.
+#include <cstdlib>
 #include "common.cuh"
 
 namespace pdgn {
@@ -75,8 +76,17 @@ __global__ void __launch_bounds__(GT) group_bwd_kernel(const float* __restrict__
 // The random 4-byte gathers of the kernels above are served by L1 at ~10+ cycles per warp load; for feature-sized C that,
 // not HBM, is the limit (3.3 TB/s = 51 % of the measured copy peak at B=35, C=256, n=m=1024, k=10).  Staging the CC
 // feature rows of one (batch, channel chunk) in shared memory turns them into 32-bank gathers, leaving the streaming of
-// the [B,C,m,k] tensor as the only HBM traffic.
-constexpr int GS_ROW_BYTES = 64 * 1024;   // shared budget for staged rows per CTA (3 CTAs / SM)
+// the [B,C,m,k] tensor as the only HBM traffic.  Small row chunks (16 KB => ~12 CTAs/SM) and a software-pipelined index
+// load keep enough stores in flight to cover the index-load -> LDS -> store latency chain.
+static int gs_row_bytes() {  // shared budget for staged rows per CTA (tuning hook: PDGN_GS_ROW_KB)
+    static int v = 0;
+    if (v == 0) {
+        const char* e = getenv("PDGN_GS_ROW_KB");
+        v = (e ? atoi(e) : 16) * 1024;  // 16 KB: 84.5 % of HBM at the C=256 stress shape (64 KB: 75 %), profiles/r01_gather_tune.txt
+    }
+    return v;
+}
+#define GS_ROW_BYTES gs_row_bytes()
 
 __global__ void __launch_bounds__(GT) group_fwd_smem_kernel(const float* __restrict__ points, const int* __restrict__ idx, int c,
                                                            int n, int mk, int cc_max, int jpart, float* __restrict__ out) {
@@ -93,12 +103,16 @@ __global__ void __launch_bounds__(GT) group_fwd_smem_kernel(const float* __restr
     const long long e_end = min((long long)mk, (long long)(blockIdx.x + 1) * jpart);
     const int* ip = idx + (size_t)bz * mk;
     float* dst0 = out + ((size_t)bz * c + c0) * mk;
-    for (long long e = (long long)blockIdx.x * jpart + threadIdx.x * 4; e < e_end; e += GT * 4) {
-        const int4 id = *reinterpret_cast<const int4*>(ip + e);
+    long long e = (long long)blockIdx.x * jpart + threadIdx.x * 4;
+    int4 id = e < e_end ? *reinterpret_cast<const int4*>(ip + e) : make_int4(0, 0, 0, 0);
+    for (; e < e_end; e += GT * 4) {
+        const long long en = e + GT * 4;  // software-pipelined index load: the next quad is in flight while this one is gathered
+        const int4 idn = en < e_end ? *reinterpret_cast<const int4*>(ip + en) : make_int4(0, 0, 0, 0);
         const float* r = rows;
         float* dst = dst0 + e;
 #pragma unroll 4
         for (int ch = 0; ch < cc; ++ch, r += n, dst += mk) st_stream4(dst, make_float4(r[id.x], r[id.y], r[id.z], r[id.w]));
+        id = idn;
     }
 }
 
