@@ -122,6 +122,15 @@ int pdgn_cd_allpairs_host(const float *A_host, const float *B_host, int na, int 
 int pdgn_emd_allpairs(const float *A, const float *B, int na, int nb, int n, int m, int row0, int row1, int col0,
                       int col1, float *out, long long ld_out, void *stream);
 
+/* ---- fused neighbourhood statistics (next row: the loss-side of get_local_pair) -------------------------------
+ * Replaces grouping + transpose/view + compute_mean_covariance (lib/pointops/functions/pointops.py:699-703,
+ * models/PDGNet_v2.py:127-134,142-147) for given kNN indices: xyz [b,n,3], idx int32 [b,m,k] ->
+ * mu [b,m,3] (mean of the k neighbours), cov [b,m,9] (their covariance, row-major 3x3, divided by k).
+ * bwd: grad_xyz [b,n,3] += adjoint of (grad_mu, grad_cov); `mu` is the forward output.  1 <= k <= 64. */
+int pdgn_local_stats_fwd(const float *xyz, const int *idx, int b, int n, int m, int k, float *mu, float *cov, void *stream);
+int pdgn_local_stats_bwd(const float *xyz, const int *idx, const float *mu, const float *grad_mu, const float *grad_cov,
+                         int b, int n, int m, int k, float *grad_xyz, void *stream);
+
 /* ---- feature-space kNN of the generator ---------------------------------------------------------------
  * Replaces bmm + torch.sort + slice in get_edge_features{,_xyz} (models/PDGNet_v2.py:449-459, :492-502).
  * x [b,c,n] -> idx int64 [b,n,k]: ranks skip..skip+k-1 of the ascending (d2, index) order of exact FP32

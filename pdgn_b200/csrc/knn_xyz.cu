@@ -450,8 +450,13 @@ static int knn_dispatch(const float* xyz, const float* new_xyz, int b, int n, in
     }
     // k <= 24 of 32 groups / k <= 48 of 64 groups keeps the expected survivor count (~G/(G-k) * k-ish) well under KS_SCAP
     if (k <= 24 && select_plan(n, k, 32, &log2ss, &gsz)) {
-        if (m > 256) return launch_select<32, 16>(xyz, new_xyz, b, n, m, k, log2ss, gsz, idx, dist2, st);
-        return launch_select<32, 8>(xyz, new_xyz, b, n, m, k, log2ss, gsz, idx, dist2, st);
+        // warps per CTA: as many as possible (they share the candidate tile) while the grid still covers the SMs --
+        // the training shapes have only 256..1024 queries per batch element
+        const long long want = 132;  // ~0.9 x SMs: one full wave of the widest CTA beats two waves of narrower ones
+        if ((long long)((m + 511) / 512) * b >= want) return launch_select<32, 16>(xyz, new_xyz, b, n, m, k, log2ss, gsz, idx, dist2, st);
+        if ((long long)((m + 255) / 256) * b >= want) return launch_select<32, 8>(xyz, new_xyz, b, n, m, k, log2ss, gsz, idx, dist2, st);
+        if ((long long)((m + 127) / 128) * b >= want) return launch_select<32, 4>(xyz, new_xyz, b, n, m, k, log2ss, gsz, idx, dist2, st);
+        return launch_select<32, 2>(xyz, new_xyz, b, n, m, k, log2ss, gsz, idx, dist2, st);
     }
     if (k <= 48 && select_plan(n, k, 64, &log2ss, &gsz)) return launch_select<64, 8>(xyz, new_xyz, b, n, m, k, log2ss, gsz, idx, dist2, st);
     const size_t smem = (size_t)3 * KG_TILE * 4 + (size_t)k * KG_T * 8;

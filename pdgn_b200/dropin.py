@@ -20,7 +20,7 @@ import runpy
 import sys
 import types
 
-from . import chamfer_loss, edge_features, evaluation_metrics, pointops
+from . import chamfer_loss, edge_features, evaluation_metrics, local_pair, pointops
 
 _REBIND = ("models.PDGNet_v2", "models.PDGNet")
 
@@ -91,6 +91,10 @@ class _RebindFinder(importlib.abc.MetaPathFinder):
 def rebind(module):
     module.get_edge_features = edge_features.get_edge_features
     module.get_edge_features_xyz = edge_features.get_edge_features_xyz
+    # the trainer's get_local_pair (PDGNet_v2.py:136-155) -> the fused op; nsample is hard-wired to 20 there (:115, :144-145)
+    for obj in list(vars(module).values()):
+        if isinstance(obj, type) and "get_local_pair" in vars(obj):
+            obj.get_local_pair = lambda self, pt1, pt2: local_pair.get_local_pair(pt1, pt2, 20)
     return module
 
 

@@ -211,3 +211,26 @@ def edge_feat_bwd(grad_ee, idx, c):
         check(L.pdgn_edge_feat_bwd_ws(grad_ee.data_ptr(), idx.data_ptr(), b, c, n, k, gx.data_ptr(), ws.data_ptr(), ws_bytes,
                                       _stream(grad_ee)), "pdgn_edge_feat_bwd_ws")
     return gx
+
+
+def local_stats_fwd(xyz, idx):
+    """xyz [b,n,3], idx int32 [b,m,k] -> (mu [b,m,3], cov [b,m,9]) of every query's k neighbours."""
+    _req(xyz, "xyz"); _req(idx, "idx", torch.int32)
+    b, n, _ = xyz.shape
+    _, m, k = idx.shape
+    mu = torch.empty((b, m, 3), dtype=torch.float32, device=xyz.device)
+    cov = torch.empty((b, m, 9), dtype=torch.float32, device=xyz.device)
+    with torch.cuda.device(xyz.device):
+        check(lib().pdgn_local_stats_fwd(xyz.data_ptr(), idx.data_ptr(), b, n, m, k, mu.data_ptr(), cov.data_ptr(), _stream(xyz)), "pdgn_local_stats_fwd")
+    return mu, cov
+
+
+def local_stats_bwd(xyz, idx, mu, grad_mu, grad_cov):
+    _req(xyz, "xyz"); _req(idx, "idx", torch.int32); _req(mu, "mu"); _req(grad_mu, "grad_mu"); _req(grad_cov, "grad_cov")
+    b, n, _ = xyz.shape
+    _, m, k = idx.shape
+    gx = torch.zeros_like(xyz)
+    with torch.cuda.device(xyz.device):
+        check(lib().pdgn_local_stats_bwd(xyz.data_ptr(), idx.data_ptr(), mu.data_ptr(), grad_mu.data_ptr(), grad_cov.data_ptr(), b, n, m, k,
+                                         gx.data_ptr(), _stream(xyz)), "pdgn_local_stats_bwd")
+    return gx

@@ -88,8 +88,25 @@ ours_group = pointops.Gen_QueryAndGroupXYZ(radius=None, nsample=20, use_xyz=Fals
 t_ours = ev_time(lambda: loss_side(ours_group, ChamferLoss(), True))
 t_ours_f = ev_time(lambda: loss_side(ours_group, ChamferLoss(), False))
 t_ref_f = ev_time(lambda: loss_side(RefGroup(), RefChamfer(), False), reps=2, warm=1)
+from pdgn_b200 import local_pair as fused  # noqa: E402
+
+
+def loss_side_fused(backward):
+    leaves = {n: p.clone().requires_grad_(backward) for n, p in pts.items()}
+    total = 0
+    for m_, n_ in sizes:
+        a, b = fused.get_local_pair(leaves[m_], leaves[n_])
+        total = total + a + b
+    if backward:
+        total.backward()
+    return total
+
+
+t_fused = ev_time(lambda: loss_side_fused(True))
+t_fused_f = ev_time(lambda: loss_side_fused(False))
 print("loss side, 6 x get_local_pair (12 kNN+group, 12 Chamfer), B=35:")
-print("  pdgn_b200  fwd+bwd %8.3f ms   fwd %8.3f ms" % (t_ours, t_ours_f))
+print("  pdgn_b200 fused get_local_pair  fwd+bwd %8.3f ms   fwd %8.3f ms" % (t_fused, t_fused_f))
+print("  pdgn_b200 op-by-op composition  fwd+bwd %8.3f ms   fwd %8.3f ms" % (t_ours, t_ours_f))
 print("  reference kernels + torch Gram Chamfer on this GPU, fwd only %8.3f ms" % t_ref_f)
 
 print("generator feature-space kNN stages (get_edge_features_xyz fwd+bwd), B=35, k=10:")

@@ -21,6 +21,9 @@ def test_reference_import_statements_resolve_to_pdgn_b200(tmp_path):
             return 'reference torch implementation'
         def get_edge_features_xyz(x, pc, k, num=-1):
             return 'reference torch implementation'
+        class PDGNet_v2(object):
+            def get_local_pair(self, pt1, pt2):
+                return 'reference composition'
     """))
     code = textwrap.dedent("""
         import sys
@@ -35,6 +38,7 @@ def test_reference_import_statements_resolve_to_pdgn_b200(tmp_path):
         assert M.misc.MARK == 'reference utils.misc'
         assert M.get_edge_features is pdgn_b200.edge_features.get_edge_features
         assert M.get_edge_features_xyz is pdgn_b200.edge_features.get_edge_features_xyz
+        assert M.PDGNet_v2.get_local_pair.__name__ == '<lambda>'      # rebound to pdgn_b200.local_pair.get_local_pair
         import pointops_cuda
         for f in ['knnquery_cuda', 'grouping_forward_cuda', 'grouping_backward_cuda', 'nearestneighbor_cuda',
                   'interpolation_forward_cuda', 'interpolation_backward_cuda']:

@@ -521,3 +521,60 @@ def test_jsd_matches_reference_golden(dev, golden):
     assert jsd == pytest.approx(float(g["jsd_value"]), rel=1e-3, abs=1e-6)
     grid, spacing = em.unit_cube_grid_point_cloud(28, True)
     assert grid.shape == (len(g["jsd_counters_smp"]), 3) and spacing == pytest.approx(1.0 / 27)
+
+
+# ------------------------------------------------------------------------------------------------ fused local statistics
+def _local_pair_reference_composition(pt1, pt2):
+    """get_local_pair exactly as models/PDGNet_v2.py:127-155 composes it, on top of the (already verified) mirrored ops."""
+    from pdgn_b200 import pointops
+    from pdgn_b200.chamfer_loss import ChamferLoss
+    group = pointops.Gen_QueryAndGroupXYZ(radius=None, nsample=20, use_xyz=False)
+    chamfer = ChamferLoss()
+
+    def mean_cov(points):
+        bs, ch, nump = points.size()
+        mu = points.mean(dim=-1, keepdim=True)
+        tmp = points - mu.repeat(1, 1, nump)
+        return mu, torch.bmm(tmp, tmp.transpose(1, 2)) / nump
+
+    b, _, m = pt1.size()
+    new_xyz = pt1.transpose(1, 2).contiguous()
+    g1 = group(pt1.transpose(1, 2).contiguous(), new_xyz).transpose(1, 2).contiguous().view(-1, 3, 20)
+    g2 = group(pt2.transpose(1, 2).contiguous(), new_xyz).transpose(1, 2).contiguous().view(-1, 3, 20)
+    mu1, var1 = mean_cov(g1)
+    mu2, var2 = mean_cov(g2)
+    return (chamfer(mu1.view(b, -1, 3), mu2.view(b, -1, 3)) / float(m), chamfer(var1.view(b, -1, 9), var2.view(b, -1, 9)) / float(m))
+
+
+@pytest.mark.parametrize("b,m,n", [(3, 256, 512), (2, 512, 2048), (2, 300, 300)])
+def test_fused_get_local_pair_matches_reference_composition(dev, b, m, n):
+    from pdgn_b200 import local_pair
+    rng = np.random.default_rng(m + n)
+    p1 = G(np.ascontiguousarray(clouds_sphere(rng, b, m, 3).transpose(0, 2, 1)), dev)
+    p2 = G(np.ascontiguousarray(clouds_sphere(rng, b, n, 3).transpose(0, 2, 1)), dev)
+    a1, a2 = p1.clone().requires_grad_(True), p2.clone().requires_grad_(True)
+    b1, b2 = p1.clone().requires_grad_(True), p2.clone().requires_grad_(True)
+    mu_f, var_f = local_pair.get_local_pair(a1, a2)
+    mu_r, var_r = _local_pair_reference_composition(b1, b2)
+    assert mu_f.item() == pytest.approx(mu_r.item(), rel=1e-5)
+    assert var_f.item() == pytest.approx(var_r.item(), rel=1e-4)
+    (mu_f + 3.0 * var_f).backward()
+    (mu_r + 3.0 * var_r).backward()
+    torch.testing.assert_close(a1.grad, b1.grad, rtol=2e-3, atol=2e-5)
+    torch.testing.assert_close(a2.grad, b2.grad, rtol=2e-3, atol=2e-5)
+
+
+def test_local_stats_against_numpy(dev):
+    from oracle import cpu as ocpu
+    from pdgn_b200 import ops
+    rng = np.random.default_rng(77)
+    xyz = clouds_uniform(rng, 2, 400, 3)
+    q = clouds_uniform(rng, 2, 90, 3)
+    idx, _ = ocpu.knn_xyz(xyz, q, 20)
+    mu, cov = ops.local_stats_fwd(G(xyz, dev), G(idx, dev))
+    grouped = np.stack([xyz[b][idx[b]] for b in range(2)]).astype(np.float64)     # [2, 90, 20, 3]
+    mu_ref = grouped.mean(axis=2)
+    t = grouped - mu_ref[:, :, None, :]
+    cov_ref = np.einsum("bjsa,bjsc->bjac", t, t) / 20.0
+    np.testing.assert_allclose(C(mu), mu_ref, rtol=1e-6, atol=1e-7)
+    np.testing.assert_allclose(C(cov).reshape(2, 90, 3, 3), cov_ref, rtol=1e-5, atol=1e-7)
