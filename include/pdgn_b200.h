@@ -118,9 +118,12 @@ int pdgn_cd_allpairs_host(const float *A_host, const float *B_host, int na, int 
  * bound as StructuralLossesBackend.ApproxMatch / MatchCost, pybind/bind.cpp:10-16) as emd_approx composes them
  * (evaluation/evaluation_metrics.py:26-31) inside _pairwise_EMD_CD_ (:110).  A [na,n,3], B [nb,m,3] ->
  *   out[(s-row0)*ld_out + (r-col0)] = match_cost(A_s, B_r) / n.
- * The n x m match matrix is never materialised.  n, m <= 2048.  No gradient (evaluation only). */
+ * The n x m match matrix is never materialised.  n, m <= 2048.  No gradient (evaluation only).
+ * workspace: pdgn_emd_allpairs_workspace(row1-row0, col1-col0, n, m) bytes of 16-byte-aligned device scratch (the tile's
+ * clouds in kd-tree leaf order, which lets the kernel skip far-apart point blocks whose weights are exact zeros). */
+size_t pdgn_emd_allpairs_workspace(int nrows, int ncols, int n, int m);
 int pdgn_emd_allpairs(const float *A, const float *B, int na, int nb, int n, int m, int row0, int row1, int col0,
-                      int col1, float *out, long long ld_out, void *stream);
+                      int col1, float *out, long long ld_out, void *workspace, size_t workspace_bytes, void *stream);
 
 /* ---- fused neighbourhood statistics (next row: the loss-side of get_local_pair) -------------------------------
  * Replaces grouping + transpose/view + compute_mean_covariance (lib/pointops/functions/pointops.py:699-703,

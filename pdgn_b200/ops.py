@@ -156,9 +156,12 @@ def emd_allpairs(A, B, rows=None, cols=None, out=None):
     c0, c1 = cols if cols is not None else (0, nb)
     if out is None:
         out = torch.empty((r1 - r0, c1 - c0), dtype=torch.float32, device=A.device)
+    L = lib()
+    ws_bytes = L.pdgn_emd_allpairs_workspace(r1 - r0, c1 - c0, n, m)
+    ws = torch.empty((ws_bytes,), dtype=torch.uint8, device=A.device)
     with torch.cuda.device(A.device):
-        check(lib().pdgn_emd_allpairs(A.data_ptr(), B.data_ptr(), na, nb, n, m, r0, r1, c0, c1, out.data_ptr(), out.stride(0),
-                                      _stream(A)), "pdgn_emd_allpairs")
+        check(L.pdgn_emd_allpairs(A.data_ptr(), B.data_ptr(), na, nb, n, m, r0, r1, c0, c1, out.data_ptr(), out.stride(0),
+                                  ws.data_ptr(), ws_bytes, _stream(A)), "pdgn_emd_allpairs")
     return out
 
 

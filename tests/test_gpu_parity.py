@@ -321,6 +321,32 @@ def test_emd_allpairs_vs_oracle(dev, na, nb, n, m, maker):
     np.testing.assert_allclose(out, ref, rtol=2e-4, atol=1e-7)
 
 
+def test_emd_block_skipping_shapes(dev):
+    """The kd-order pre-sort + bounding-box skip drops only exact-zero terms: clouds where almost every block is skipped
+    (two far-apart tight clusters, large extent), where none is (tiny extent), and degenerate ones (all points equal,
+    collinear) still match the CPU restatement."""
+    from oracle import cpu as ocpu
+    from pdgn_b200 import ops
+    rng = np.random.default_rng(77)
+    n = 1024
+    blobs = np.concatenate([rng.normal(-1.5, 0.05, (2, n // 2, 3)), rng.normal(1.5, 0.05, (2, n // 2, 3))], axis=1)
+    wide = rng.uniform(-4, 4, (2, n, 3))
+    tiny = rng.uniform(-0.01, 0.01, (2, n, 3))
+    same = np.broadcast_to(rng.uniform(-1, 1, (2, 1, 3)), (2, n, 3)).copy()
+    line = np.zeros((2, n, 3)); line[..., 0] = rng.uniform(-1, 1, (2, n))
+    for A in (blobs, wide, tiny, same, line):
+        for B in (blobs, wide, line):
+            A32, B32 = A.astype(np.float32), B.astype(np.float32)
+            out = C(ops.emd_allpairs(G(A32, dev), G(B32, dev)))
+            ref = (ocpu.emd_cost(np.repeat(A32, 2, axis=0), np.tile(B32, (2, 1, 1))) / np.float32(n)).reshape(2, 2)
+            np.testing.assert_allclose(out, ref, rtol=3e-4, atol=1e-6)
+    # order independence: permuting the points of a cloud changes nothing but rounding
+    perm = rng.permutation(n)
+    a = ops.emd_allpairs(G(wide.astype(np.float32), dev), G(blobs.astype(np.float32), dev))
+    b = ops.emd_allpairs(G(wide[:, perm].astype(np.float32), dev), G(blobs.astype(np.float32), dev))
+    torch.testing.assert_close(a, b, rtol=0, atol=0)  # same kd order -> same summation order -> same bits
+
+
 def test_emd_against_recompiled_reference(dev):
     """The reference's own ApproxMatch + MatchCost kernels (recompiled for sm_100a) on expanded pairs, as
     _pairwise_EMD_CD_ calls them (evaluation_metrics.py:101-110)."""
