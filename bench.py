@@ -18,6 +18,7 @@ One JSON line on rank 0:
 `--impl reference` times only the CPU formulation (rank 0; other ranks exit 0).
 """
 import argparse
+import datetime
 import json
 import os
 import statistics
@@ -50,7 +51,7 @@ def make_clouds(seed, n=N_CLOUDS, npts=N_PTS):
 
 class ClockSampler:
     """nvidia-smi clocks / throttle reasons DURING the timed region (B200_PROFILING.md recipe)."""
-    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+    Q = ("timestamp,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
          "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
 
     def __init__(self, index):
@@ -59,11 +60,13 @@ class ClockSampler:
     def start(self):
         try:
             self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q, "--format=csv,noheader,nounits",
-                                          "-lms", "100"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+                                          "-lms", os.environ.get("PDGN_BENCH_SMI_MS", "100")], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
         except OSError:
             self.proc = None
 
-    def stop(self):
+    def stop(self, window=None):
+        """window = (t0, t1) wall-clock seconds: only samples taken inside it are used (the sampler is started before the
+        warm-up so that nvidia-smi's own start-up does not fall into the timed region)."""
         if self.proc is None:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
         self.proc.terminate()
@@ -72,18 +75,28 @@ class ClockSampler:
         except subprocess.TimeoutExpired:
             self.proc.kill()
             out, _ = self.proc.communicate()
-        sm, mx, pw, reasons = [], [], [], set()
+        rows = []
         for line in out.splitlines():
             f = [x.strip() for x in line.split(",")]
             if len(f) < 9:
                 continue
             try:
-                sm.append(float(f[1])); mx.append(float(f[2])); pw.append(float(f[3]))
+                vals = (float(f[1]), float(f[2]), float(f[3]))
             except ValueError:
                 continue
-            for name, val in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), f[5:9]):
-                if val.lower().startswith("active"):
-                    reasons.add(name)
+            try:
+                ts = datetime.datetime.strptime(f[0], "%Y/%m/%d %H:%M:%S.%f").timestamp()
+            except ValueError:
+                ts = None
+            flags = [name for name, val in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), f[5:9])
+                     if val.lower().startswith("active")]
+            rows.append((ts, vals, flags))
+        inside = [r for r in rows if window is not None and r[0] is not None and window[0] <= r[0] <= window[1]]
+        used = inside if inside else rows  # unparsable timestamps: fall back to every sample (warm-up included)
+        sm, mx, pw, reasons = [], [], [], set()
+        for _, vals, flags in used:
+            sm.append(vals[0]); mx.append(vals[1]); pw.append(vals[2])
+            reasons.update(flags)
         if not sm:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["no samples"]}
         return {"sm_mhz": statistics.median(sm), "sm_max_mhz": max(mx), "power_w_max": max(pw), "samples": len(sm),
@@ -211,26 +224,33 @@ def main():
         sync_all()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record()
+        marks = []
         for _ in range(k):
             flush.zero_()
             out = step()
+            marks.append(torch.cuda.Event(enable_timing=True))
+            marks[-1].record()
         e1.record()
         sync_all()
         ms = torch.tensor([e0.elapsed_time(e1)], device=dev)
         if world > 1:
             dist.all_reduce(ms, op=dist.ReduceOp.MAX)
-        return ms.item(), out
+        per_step = [round(a.elapsed_time(b), 2) for a, b in zip([e0] + marks[:-1], marks)]
+        return ms.item(), out, per_step
 
-    for _ in range(args.warmup):
-        step_device()
     sampler = ClockSampler(local_rank)
     if rank == 0:
         sampler.start()
-    ms_total, out = timed(step_device, args.steps)
-    clocks = sampler.stop() if rank == 0 else None
+    for _ in range(args.warmup):
+        flush.zero_()  # warm-up steps are the timed steps, L2 flush included (its fill kernel is lazily loaded on first use)
+        step_device()
+    t_begin = time.time()
+    ms_total, out, step_ms = timed(step_device, args.steps)
+    clocks = sampler.stop((t_begin, time.time())) if rank == 0 else None
     for _ in range(min(args.warmup, 2)):
+        flush.zero_()
         step_e2e()
-    ms_e2e, out_e2e = timed(step_e2e, args.steps)
+    ms_e2e, out_e2e, step_ms_e2e = timed(step_e2e, args.steps)
 
     # the dominant kernel alone (rank's own tile, no collective): CUDA events around the C-ABI launch.  The two pack
     # kernels in the same call are ~0.01 % of it (profiles/: launch list).
@@ -279,7 +299,7 @@ def main():
     }
     line = {
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
-        "ms_per_step": ms_total / args.steps, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
+        "ms_per_step": ms_total / args.steps, "step_ms": step_ms, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
         "dtype": "f32", "data": "synthetic",
         "config": {"workload": WORKLOAD if nc == N_CLOUDS else "allpairs_cd_%dx%d_clouds_2048pts" % (nc, nc),
                    "clouds": [nc, nc], "points_per_cloud": N_PTS, "partition": "%dx%d rank grid, all_gather of scalars" % pdist.rank_grid(world),
