@@ -14,8 +14,11 @@
 //   * Each distance is computed once and feeds both directions: the row minimum stays in the thread's
 //     registers (FMNMX3 over two candidates), the column minimum is folded over the thread's 16 rows
 //     (FMNMX3), reduced across the warp with one CREDUX.MIN on the bit pattern (distances are >= 0 so uint
-//     order == float order) and merged across the half's 4 warps with one shared-memory ATOMS.MIN.
+//     order == float order) and stored to the warp's own column array (one STS.128 per 4 candidates); the half's
+//     4 warps are merged when the cloud pair is folded.  Clouds of more than 2048 points walk several row blocks and
+//     merge through shared-memory ATOMS.MIN instead.
 //   * Per cloud pair only one scalar leaves the SM: (sum_i rowmin + sum_j colmin) / npts.
+#include <cstdlib>
 #include "cd_kernel.cuh"
 
 namespace pdgn {
@@ -24,10 +27,26 @@ namespace pdgn {
 constexpr int CD_R = 16;      // rows per thread
 constexpr int CD_NH = 2;      // halves (A clouds) per CTA
 constexpr int CD_MINB = 2;    // CTAs per SM the register allocation must allow
-constexpr int CD_VARIANT = CDV_PRED_RED | CDV_PREFETCH;  // +2.3 % over the plain loop (profiles/r01_cd_tune_*.txt)
+constexpr int CD_VARIANT_BIG = CDV_PRED_RED | CDV_PREFETCH;   // npts > 2048: several row blocks merge their column minima by ATOMS.MIN
+// npts <= 2048 (every PDGN shape): per-warp column arrays written with plain STS.128 (no atomics, no branches in the inner
+// loop); row minima as VIMNMX3.U32 on the bit patterns (d2 >= +0, so the order is the same; ptxas schedules this mix best:
+// 0.707 vs 0.695 of the issue roofline, profiles/r01_cd_tune_c.txt)
+constexpr int CD_VARIANT = CDV_PREFETCH | CDV_WARPCOL | CDV_IMIN_ROW;
 constexpr int CD_THREADS = CD_NH * CD_HALF;
-#define PDGN_CD_KERNEL cd_allpairs_kernel<CD_R, CD_NH, CD_MINB, CD_VARIANT, false>
-#define PDGN_CD_KERNEL_SYM cd_allpairs_kernel<CD_R, CD_NH, CD_MINB, CD_VARIANT, true>
+
+template <int VAR>
+static int cd_launch(bool sym, dim3 grid, size_t smem, cudaStream_t st, const float* PA, const float* PB, int nrows, int ncols,
+                     int npts, int npad, int rstrip, float* out, long long ld_out) {
+    if (sym) {
+        PDGN_CUDA(cudaFuncSetAttribute(cd_allpairs_kernel<CD_R, CD_NH, CD_MINB, VAR, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        cd_allpairs_kernel<CD_R, CD_NH, CD_MINB, VAR, true><<<grid, CD_THREADS, smem, st>>>(PA, PB, nrows, ncols, npts, npad, rstrip, out, ld_out);
+    } else {
+        PDGN_CUDA(cudaFuncSetAttribute(cd_allpairs_kernel<CD_R, CD_NH, CD_MINB, VAR, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        cd_allpairs_kernel<CD_R, CD_NH, CD_MINB, VAR, false><<<grid, CD_THREADS, smem, st>>>(PA, PB, nrows, ncols, npts, npad, rstrip, out, ld_out);
+    }
+    PDGN_CHECK_LAUNCH();
+    return PDGN_OK;
+}
 
 static int cd_num_sms() {
     static int sms = 0;
@@ -81,21 +100,28 @@ extern "C" int pdgn_cd_allpairs(const float* A, const float* B, int na, int nb, 
         PDGN_CHECK_LAUNCH();
     }
 
-    const size_t smem = cd_smem_bytes<CD_NH, CD_VARIANT>(npad);
-    PDGN_CUDA(cudaFuncSetAttribute(PDGN_CD_KERNEL, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    PDGN_CUDA(cudaFuncSetAttribute(PDGN_CD_KERNEL_SYM, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     const int spairs = (nrows + CD_NH - 1) / CD_NH;
     if (spairs > 65535) return PDGN_ERR_UNSUPPORTED;
     // enough CTAs that the last partial wave is a small fraction of the run; each CTA walks `rstrip` B clouds
-    const int target = (sym ? 128 : 64) * CD_MINB * cd_num_sms();  // ~64 waves: tail <= ~1.5 %; sym: half the CTAs exit at once
+    static const int waves = [] {  // tuning hook
+        const char* e = getenv("PDGN_CD_WAVES");
+        const int v = e ? atoi(e) : 0;
+        return v > 0 ? v : 64;
+    }();
+    const int target = (sym ? 2 : 1) * waves * CD_MINB * cd_num_sms();  // ~64 waves: tail <= ~1.5 %; sym: half the CTAs exit at once
     int strips = (target + spairs - 1) / spairs;
     if (strips > ncols) strips = ncols;
     if (strips < 1) strips = 1;
     const int rstrip = (ncols + strips - 1) / strips;
     strips = (ncols + rstrip - 1) / rstrip;
-    if (sym) PDGN_CD_KERNEL_SYM<<<dim3(strips, spairs), CD_THREADS, smem, st>>>(PA, PB, nrows, ncols, npts, npad, rstrip, out, ld_out);
-    else PDGN_CD_KERNEL<<<dim3(strips, spairs), CD_THREADS, smem, st>>>(PA, PB, nrows, ncols, npts, npad, rstrip, out, ld_out);
-    PDGN_CHECK_LAUNCH();
+    const dim3 grid(strips, spairs);
+    static const bool force_big = getenv("PDGN_CD_ATOMIC_COLMIN") != nullptr;  // tuning hook: the shared-atomic variant for every size
+    int rc;
+    if (npts <= CD_R * CD_HALF && !force_big)
+        rc = cd_launch<CD_VARIANT>(sym, grid, cd_smem_bytes<CD_NH, CD_VARIANT>(npad), st, PA, PB, nrows, ncols, npts, npad, rstrip, out, ld_out);
+    else
+        rc = cd_launch<CD_VARIANT_BIG>(sym, grid, cd_smem_bytes<CD_NH, CD_VARIANT_BIG>(npad), st, PA, PB, nrows, ncols, npts, npad, rstrip, out, ld_out);
+    if (rc != PDGN_OK) return rc;
     if (sym) {
         cd_mirror_kernel<<<dim3((nrows + 31) / 32, (nrows + 7) / 8), dim3(32, 8), 0, st>>>(out, nrows, ld_out);
         PDGN_CHECK_LAUNCH();

@@ -14,6 +14,8 @@ constexpr int CDV_PRED_RED = 1;    // predicated red.shared.min (inline PTX) ins
 constexpr int CDV_PREFETCH = 2;    // software-pipelined LDS.128 of the next 4 candidates
 constexpr int CDV_RED4 = 4;        // one shared atomic per 4 candidates (lanes 0..3) instead of one per 2
 constexpr int CDV_AOS = 8;         // candidates staged as float4 (x,y,z,0): x/z always land in even registers, y in odd
+constexpr int CDV_WARPCOL = 16;    // every warp owns a column-minimum array: one STS.128 per 4 candidates, no shared atomics,
+                                   // no initialisation (needs a single row block: npts <= R*128, and 4x the column storage)
 
 // AoS [cloud][npts][3] -> SoA planes [cloud][3][npad]; pad entries replicate point 0 (harmless for minima).
 __global__ void cd_pack_kernel(const float* __restrict__ src, int cloud0, int npts, int npad, float* __restrict__ dst) {
@@ -43,15 +45,32 @@ __device__ __forceinline__ void red_min_shared_pred(unsigned* addr, unsigned v, 
         "@p red.shared.min.u32 [%0], %1;\n\t}" ::"r"(smem_u32(addr)), "r"(v), "r"((unsigned)pred) : "memory");
 }
 
+// ablation switches for tools/cd_tune.cu only (results are WRONG with them; they price the two minimum streams)
+constexpr int CDV_ABL_NOCOL = 32;  // no column minima
+constexpr int CDV_ABL_NOROW = 64;  // no row minima
+
+constexpr int CDV_IMIN = 128;      // minima as unsigned-integer min3 on the bit patterns (d2 >= +0: same order)
+constexpr int CDV_IMIN_ROW = 256;  // ... row minima only
+constexpr int CDV_IMIN_COL = 512;  // ... column minima only
+constexpr int CDV_UNROLL2 = 1024;  // candidate loop unrolled twice (8 candidates per iteration)
+
+template <int VAR, int WHICH>
+__device__ __forceinline__ float cd_min3(float a, float b, float c) {
+    if (VAR & (CDV_IMIN | WHICH)) return __uint_as_float(min(min(__float_as_uint(a), __float_as_uint(b)), __float_as_uint(c)));
+    return min3(a, b, c);
+}
+
 // Two candidates against the thread's R rows: updates the row minima, returns the two column partial minima.
-template <int R>
+template <int R, int VAR = 0>
 __device__ __forceinline__ void cd_two_candidates(const float (&qx)[R], const float (&qy)[R], const float (&qz)[R], float (&rowmin)[R],
                                                   float x0, float y0, float z0, float x1, float y1, float z1, float& c0, float& c1) {
     {
         const float a0 = d2_xyz(qx[0], qy[0], qz[0], x0, y0, z0), a1 = d2_xyz(qx[0], qy[0], qz[0], x1, y1, z1);
         const float b0 = d2_xyz(qx[1], qy[1], qz[1], x0, y0, z0), b1 = d2_xyz(qx[1], qy[1], qz[1], x1, y1, z1);
-        rowmin[0] = min3(rowmin[0], a0, a1);
-        rowmin[1] = min3(rowmin[1], b0, b1);
+        if (!(VAR & CDV_ABL_NOROW)) {
+            rowmin[0] = cd_min3<VAR, CDV_IMIN_ROW>(rowmin[0], a0, a1);
+            rowmin[1] = cd_min3<VAR, CDV_IMIN_ROW>(rowmin[1], b0, b1);
+        }
         c0 = fminf(a0, b0);
         c1 = fminf(a1, b1);
     }
@@ -60,10 +79,14 @@ __device__ __forceinline__ void cd_two_candidates(const float (&qx)[R], const fl
         const float a0 = d2_xyz(qx[k], qy[k], qz[k], x0, y0, z0), a1 = d2_xyz(qx[k], qy[k], qz[k], x1, y1, z1);
         const float b0 = d2_xyz(qx[k + 1], qy[k + 1], qz[k + 1], x0, y0, z0);
         const float b1 = d2_xyz(qx[k + 1], qy[k + 1], qz[k + 1], x1, y1, z1);
-        rowmin[k] = min3(rowmin[k], a0, a1);
-        rowmin[k + 1] = min3(rowmin[k + 1], b0, b1);
-        c0 = min3(c0, a0, b0);
-        c1 = min3(c1, a1, b1);
+        if (!(VAR & CDV_ABL_NOROW)) {
+            rowmin[k] = cd_min3<VAR, CDV_IMIN_ROW>(rowmin[k], a0, a1);
+            rowmin[k + 1] = cd_min3<VAR, CDV_IMIN_ROW>(rowmin[k + 1], b0, b1);
+        }
+        if (!(VAR & CDV_ABL_NOCOL)) {
+            c0 = cd_min3<VAR, CDV_IMIN_COL>(c0, a0, b0);
+            c1 = cd_min3<VAR, CDV_IMIN_COL>(c1, a1, b1);
+        }
     }
 }
 
@@ -72,16 +95,21 @@ template <int R, int VAR>
 __device__ __forceinline__ void cd_four_candidates(const float (&qx)[R], const float (&qy)[R], const float (&qz)[R], float (&rowmin)[R],
                                                    const float4& X, const float4& Y, const float4& Z, unsigned* col, int lane) {
     float c0, c1, c2, c3;
-    cd_two_candidates<R>(qx, qy, qz, rowmin, X.x, Y.x, Z.x, X.y, Y.y, Z.y, c0, c1);
+    cd_two_candidates<R, VAR>(qx, qy, qz, rowmin, X.x, Y.x, Z.x, X.y, Y.y, Z.y, c0, c1);
     const unsigned r0 = __reduce_min_sync(kFull, __float_as_uint(c0));
     const unsigned r1 = __reduce_min_sync(kFull, __float_as_uint(c1));
-    if (!(VAR & CDV_RED4)) {
+    if (!(VAR & (CDV_RED4 | CDV_WARPCOL))) {
         if (VAR & CDV_PRED_RED) red_min_shared_pred(col + lane, lane ? r1 : r0, lane < 2);
         else if (lane < 2) atomicMin(col + lane, lane ? r1 : r0);
     }
-    cd_two_candidates<R>(qx, qy, qz, rowmin, X.z, Y.z, Z.z, X.w, Y.w, Z.w, c2, c3);
+    cd_two_candidates<R, VAR>(qx, qy, qz, rowmin, X.z, Y.z, Z.z, X.w, Y.w, Z.w, c2, c3);
     const unsigned r2 = __reduce_min_sync(kFull, __float_as_uint(c2));
     const unsigned r3 = __reduce_min_sync(kFull, __float_as_uint(c3));
+    if (VAR & CDV_WARPCOL) {
+        // this warp visits each candidate exactly once per cloud pair: its column minimum is final, plain store
+        if (lane == 0) *reinterpret_cast<uint4*>(col) = make_uint4(r0, r1, r2, r3);
+        return;
+    }
     if (VAR & CDV_RED4) {
         const unsigned v = lane == 0 ? r0 : lane == 1 ? r1 : lane == 2 ? r2 : r3;
         if (VAR & CDV_PRED_RED) red_min_shared_pred(col + lane, v, lane < 4);
@@ -97,7 +125,7 @@ template <int R, int VAR>
 __device__ __forceinline__ void cd_two_candidates_aos(const float (&qx)[R], const float (&qy)[R], const float (&qz)[R], float (&rowmin)[R],
                                                       const float4& P0, const float4& P1, unsigned* col, int lane) {
     float c0, c1;
-    cd_two_candidates<R>(qx, qy, qz, rowmin, P0.x, P0.y, P0.z, P1.x, P1.y, P1.z, c0, c1);
+    cd_two_candidates<R, VAR>(qx, qy, qz, rowmin, P0.x, P0.y, P0.z, P1.x, P1.y, P1.z, c0, c1);
     const unsigned r0 = __reduce_min_sync(kFull, __float_as_uint(c0));
     const unsigned r1 = __reduce_min_sync(kFull, __float_as_uint(c1));
     if (VAR & CDV_PRED_RED) red_min_shared_pred(col + lane, lane ? r1 : r0, lane < 2);
@@ -113,8 +141,9 @@ cd_allpairs_kernel(const float* __restrict__ PA, const float* __restrict__ PB, i
     extern __shared__ __align__(128) unsigned char smem_raw[];
     constexpr int STAGE = ((VAR & CDV_AOS) ? 4 : 3) * CD_TILE;                // floats per stage
     float* tile = reinterpret_cast<float*>(smem_raw);                         // [2 stages][3 planes][CD_TILE] or [2][CD_TILE] float4
-    unsigned* colmin = reinterpret_cast<unsigned*>(tile + 2 * STAGE);         // [NH][npad]
-    float* red = reinterpret_cast<float*>(colmin + NH * (size_t)npad);        // [NH][4 warps]
+    constexpr int NCOL = (VAR & CDV_WARPCOL) ? 4 : 1;                         // column arrays per half
+    unsigned* colmin = reinterpret_cast<unsigned*>(tile + 2 * STAGE);         // [NH][npad], WARPCOL: [NH][4 warps][npad]
+    float* red = reinterpret_cast<float*>(colmin + NH * NCOL * (size_t)npad); // [NH][4 warps]
     uint64_t* bars = reinterpret_cast<uint64_t*>(red + NH * 4);              // [2 stages]
 
     const int tid = threadIdx.x, half = tid >> 7, ht = tid & (CD_HALF - 1), lane = tid & 31, hw = ht >> 5;
@@ -129,9 +158,11 @@ cd_allpairs_kernel(const float* __restrict__ PA, const float* __restrict__ PB, i
     const int nrb = (npts + ROWS - 1) / ROWS;
     const int ncb = (npad + CD_TILE - 1) / CD_TILE;
     const int ntiles = (r_end - r_begin) * nrb * ncb;
-    unsigned* mycol = colmin + (size_t)half * npad;
+    unsigned* halfcol = colmin + (size_t)half * NCOL * npad;
+    unsigned* mycol = (VAR & CDV_WARPCOL) ? halfcol + (size_t)hw * npad : halfcol;
 
-    for (int j = ht; j < npad; j += CD_HALF) mycol[j] = CD_INF_BITS;
+    if (!(VAR & CDV_WARPCOL))
+        for (int j = ht; j < npad; j += CD_HALF) mycol[j] = CD_INF_BITS;
     if (tid == 0) {
         mbar_init(&bars[0], 1);
         mbar_init(&bars[1], 1);
@@ -208,7 +239,7 @@ cd_allpairs_kernel(const float* __restrict__ PA, const float* __restrict__ PB, i
                     float4 X = *reinterpret_cast<const float4*>(st);
                     float4 Y = *reinterpret_cast<const float4*>(st + CD_TILE);
                     float4 Z = *reinterpret_cast<const float4*>(st + 2 * CD_TILE);
-#pragma unroll 1
+#pragma unroll((VAR & CDV_UNROLL2) ? 2 : 1)
                     for (int j = 0; j < cnt; j += 4) {
                         const int jn = (j + 4 < cnt) ? j + 4 : j;  // last iteration re-reads its own quad
                         const float4 Xn = *reinterpret_cast<const float4*>(st + jn);
@@ -238,9 +269,14 @@ cd_allpairs_kernel(const float* __restrict__ PA, const float* __restrict__ PB, i
                 if (k < nvalid) total += rowmin[k];
         }
         // cloud pair (s, r) complete: fold this half's column minima, reset them for the next r
-        for (int j = ht; j < npad; j += CD_HALF) {
-            if (j < npts) total += __uint_as_float(mycol[j]);
-            mycol[j] = CD_INF_BITS;
+        if (VAR & CDV_WARPCOL) {
+            for (int j = ht; j < npts; j += CD_HALF)
+                total += __uint_as_float(min(min(halfcol[j], halfcol[npad + j]), min(halfcol[2 * npad + j], halfcol[3 * npad + j])));
+        } else {
+            for (int j = ht; j < npad; j += CD_HALF) {
+                if (j < npts) total += __uint_as_float(mycol[j]);
+                mycol[j] = CD_INF_BITS;
+            }
         }
         total = warp_sum(total);
         if (lane == 0) red[half * 4 + hw] = total;
@@ -260,7 +296,8 @@ __global__ void cd_mirror_kernel(float* __restrict__ out, int n, long long ld) {
 
 template <int NH, int VAR = 0>
 constexpr size_t cd_smem_bytes(int npad) {
-    return (size_t)(2 * ((VAR & CDV_AOS) ? 4 : 3) * CD_TILE + NH * (size_t)npad + NH * 4) * 4 + 2 * sizeof(uint64_t);
+    return (size_t)(2 * ((VAR & CDV_AOS) ? 4 : 3) * CD_TILE + NH * ((VAR & CDV_WARPCOL) ? 4 : 1) * (size_t)npad + NH * 4) * 4 +
+           2 * sizeof(uint64_t);
 }
 
 }  // namespace pdgn

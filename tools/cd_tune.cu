@@ -64,6 +64,20 @@ int main(int argc, char** argv) {
     run<16, 2, 2, 0>("base", PA, PB, PB4, n, npts, npad, out, nullptr, sms);
     std::vector<float> ref((size_t)n * n); CK(cudaMemcpy(ref.data(), out, ref.size() * 4, cudaMemcpyDeviceToHost));
     run<16, 2, 2, 3>("pred-red+prefetch", PA, PB, PB4, n, npts, npad, out, ref.data(), sms);
+    run<16, 2, 2, 18>("prefetch+warpcol (shipped)", PA, PB, PB4, n, npts, npad, out, ref.data(), sms);
+    run<16, 2, 2, 16>("warpcol", PA, PB, PB4, n, npts, npad, out, ref.data(), sms);
+    run<16, 2, 2, 16 + 128>("warpcol + integer min3", PA, PB, PB4, n, npts, npad, out, ref.data(), sms);
+    run<16, 2, 2, 18 + 128>("prefetch+warpcol + integer min3", PA, PB, PB4, n, npts, npad, out, ref.data(), sms);
+    run<16, 2, 2, 18 + 256>("prefetch+warpcol + imin rows", PA, PB, PB4, n, npts, npad, out, ref.data(), sms);
+    run<16, 2, 2, 18 + 512>("prefetch+warpcol + imin cols", PA, PB, PB4, n, npts, npad, out, ref.data(), sms);
+    run<16, 2, 2, 16 + 256>("warpcol + imin rows", PA, PB, PB4, n, npts, npad, out, ref.data(), sms);
+    run<16, 2, 2, 16 + 512>("warpcol + imin cols", PA, PB, PB4, n, npts, npad, out, ref.data(), sms);
+    run<16, 2, 2, 3 + 128>("pred-red+prefetch + imin", PA, PB, PB4, n, npts, npad, out, ref.data(), sms);
+    run<16, 2, 2, 18 + 256 + 1024>("prefetch+warpcol+imin rows+unroll2", PA, PB, PB4, n, npts, npad, out, ref.data(), sms);
+    run<16, 2, 2, 18 + 1024>("prefetch+warpcol+unroll2", PA, PB, PB4, n, npts, npad, out, ref.data(), sms);
+    run<16, 2, 2, 18 + 128 + 1024>("prefetch+warpcol+imin+unroll2", PA, PB, PB4, n, npts, npad, out, ref.data(), sms);
+    run<16, 2, 2, 18 + 32>("ABLATION no col-min", PA, PB, PB4, n, npts, npad, out, ref.data(), sms);
+    run<16, 2, 2, 18 + 64>("ABLATION no row-min", PA, PB, PB4, n, npts, npad, out, ref.data(), sms);
     run<16, 2, 2, 8>("aos", PA, PB, PB4, n, npts, npad, out, ref.data(), sms);
     run<16, 2, 2, 9>("aos+pred-red", PA, PB, PB4, n, npts, npad, out, ref.data(), sms);
     run<16, 2, 2, 11>("aos+pred-red+prefetch", PA, PB, PB4, n, npts, npad, out, ref.data(), sms);
