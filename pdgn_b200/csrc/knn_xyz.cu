@@ -23,6 +23,7 @@
 //   A survivor overflow (adversarial ties / clustering / fewer than k finite candidates) sends that one query to
 //   an exact serial scan, so the result is always exact.
 // Generic path (knn_generic_kernel): any k <= 128, any n; threshold-guarded insertion into a shared-memory list.
+#include <cstdlib>
 #include "common.cuh"
 
 namespace pdgn {
@@ -197,14 +198,14 @@ __device__ __forceinline__ void bitonic_sort_regs(float (&v)[N]) {
 }
 
 // Cooperative load of candidates [j0, j0+cnt) of one batch element, AoS global -> SoA shared, tail padded to a
-// multiple of 4 with NaN (a NaN distance is never a minimum).
+// multiple of 16 with NaN (a NaN distance is never a minimum).
 template <int THREADS>
 __device__ __forceinline__ void ks_load_tile(float* tile, const float* __restrict__ pb, int j0, int cnt, int t) {
     for (int e = t; e < cnt * 3; e += THREADS) {
         const int j = e / 3, c = e - j * 3;
         tile[c * KS_TILE + j] = pb[(size_t)j0 * 3 + e];
     }
-    const int cnt4 = (cnt + 3) & ~3;
+    const int cnt4 = (cnt + 15) & ~15;  // pass 1 walks blocks of 16
     if (t < cnt4 - cnt) {
         const float nanv = __int_as_float(0x7fc00000);
         tile[cnt + t] = nanv;
@@ -214,16 +215,21 @@ __device__ __forceinline__ void ks_load_tile(float* tile, const float* __restric
 }
 
 // per-warp shared block
+struct KsSelect {                      // scratch of the query being selected (pass 2)
+    unsigned long long key[KS_SCAP];   // survivors: (d2 bits << 32) | candidate index -- d2 >= 0, so unsigned order of the
+                                       //   key == the reference's (d2, index) order
+    unsigned short plist[KS_NSUB];     // subgroups that may hold survivors
+};
 template <int G>
 struct alignas(16) KsWarp {
     unsigned short sub[KS_NSUB][32];   // [subgroup][(query + subgroup) & 31]  bf16, rounded down  (swizzled: both the
                                        //   lane=query writes and the lane=subgroup reads are bank-conflict free)
-    unsigned short grp[G][32];         // [group][query]  bf16, rounded up
-    unsigned long long key[KS_SCAP];   // survivors of the query being selected: (d2 bits << 32) | candidate index --
-                                       //   d2 >= 0, so unsigned order of the key == the reference's (d2, index) order
-    unsigned short plist[KS_NSUB];     // subgroups that may hold survivors
-    int nsurv;                         // survivor counter of the query being selected
+    union {                            // the group minima are dead once every lane holds its bound tau in a register
+        unsigned short grp[G][32];     // [group][query]  bf16, rounded up (pass 1 -> bound)
+        KsSelect sel;                  // pass 2
+    };
 };
+static_assert(sizeof(KsSelect) <= sizeof(unsigned short) * 32 * 32, "KsSelect must fit under the group minima");
 
 template <int G, int NWARPS>
 __global__ void __launch_bounds__(NWARPS * 32) knn_select_kernel(const float* __restrict__ xyz, const float* __restrict__ new_xyz,
@@ -245,31 +251,20 @@ __global__ void __launch_bounds__(NWARPS * 32) knn_select_kernel(const float* __
     const float qx = qp[0], qy = qp[1], qz = qp[2];
 
     for (int g = ng; g < G; ++g) wsm->grp[g][lane] = 0x7f80;  // +inf for groups that do not exist
+    for (int sg = nsub; sg < KS_NSUB; ++sg) wsm->sub[sg][lane] = 0xffff;  // subgroups that do not exist never pass the bound
 
     // ---------------- pass 1: subgroup / group minima (lane = query)
+    // Candidates are walked in blocks of 16 (4 quads, fully unrolled, each quad loaded one quad ahead); a block yields its
+    // four quad minima, which are then emitted at the subgroup granularity (ss = 4, 8, 16, or a multiple of 16).
     {
         float gmn = kInf;
         int gleft = gsz;                                   // subgroups left in the current group
         unsigned short* subrow = &wsm->sub[0][0];          // row of the current subgroup
         unsigned short* grow = &wsm->grp[0][lane];
         int col = lane;                                    // (lane + sg) & 31
-        for (int j0 = 0; j0 < n; j0 += KS_TILE) {
-            const int cnt = min(KS_TILE, n - j0);
-            __syncthreads();
-            ks_load_tile<THREADS>(tile, pb, j0, cnt, t);
-            __syncthreads();
-            for (int jb = 0; jb < cnt; jb += ss) {
-                const int je = min(cnt, jb + ss);
-                float mn = kInf;
-#pragma unroll 4
-                for (int j = jb; j < je; j += 4) {
-                    const float4 X = *reinterpret_cast<const float4*>(tile + j);
-                    const float4 Y = *reinterpret_cast<const float4*>(tile + KS_TILE + j);
-                    const float4 Z = *reinterpret_cast<const float4*>(tile + 2 * KS_TILE + j);
-                    const float d0 = d2_xyz(qx, qy, qz, X.x, Y.x, Z.x), d1 = d2_xyz(qx, qy, qz, X.y, Y.y, Z.y);
-                    const float d2 = d2_xyz(qx, qy, qz, X.z, Y.z, Z.z), d3 = d2_xyz(qx, qy, qz, X.w, Y.w, Z.w);
-                    mn = min3(min3(mn, d0, d1), d2, d3);
-                }
+        int sgi = 0;                                       // subgroups emitted so far
+        auto emit = [&](float mn) {
+            if (sgi < nsub) {                              // (the NaN padding of the last block can start an extra one)
                 subrow[col] = (unsigned short)(__float_as_uint(mn) >> 16);   // toward zero = down (mn >= 0)
                 subrow += 32;
                 col = (col + 1) & 31;
@@ -280,8 +275,52 @@ __global__ void __launch_bounds__(NWARPS * 32) knn_select_kernel(const float* __
                     gmn = kInf;
                     gleft = gsz;
                 }
+                ++sgi;
+            }
+        };
+        float acc = kInf;                                  // ss > 16: minimum of the blocks of the current subgroup
+        for (int j0 = 0; j0 < n; j0 += KS_TILE) {
+            const int cnt = min(KS_TILE, n - j0);
+            __syncthreads();
+            ks_load_tile<THREADS>(tile, pb, j0, cnt, t);
+            __syncthreads();
+            const int cnt16 = (cnt + 15) & ~15;
+            float4 X = *reinterpret_cast<const float4*>(tile);
+            float4 Y = *reinterpret_cast<const float4*>(tile + KS_TILE);
+            float4 Z = *reinterpret_cast<const float4*>(tile + 2 * KS_TILE);
+            for (int jb = 0; jb < cnt16; jb += 16) {
+                float mq[4];
+#pragma unroll
+                for (int q = 0; q < 4; ++q) {
+                    const int jn = q < 3 ? jb + 4 * q + 4 : min(jb + 16, cnt16 - 4);
+                    const float4 Xn = *reinterpret_cast<const float4*>(tile + jn);
+                    const float4 Yn = *reinterpret_cast<const float4*>(tile + KS_TILE + jn);
+                    const float4 Zn = *reinterpret_cast<const float4*>(tile + 2 * KS_TILE + jn);
+                    const float d0 = d2_xyz(qx, qy, qz, X.x, Y.x, Z.x), d1 = d2_xyz(qx, qy, qz, X.y, Y.y, Z.y);
+                    const float d2 = d2_xyz(qx, qy, qz, X.z, Y.z, Z.z), d3 = d2_xyz(qx, qy, qz, X.w, Y.w, Z.w);
+                    mq[q] = fminf(min3(d0, d1, d2), d3);
+                    X = Xn; Y = Yn; Z = Zn;
+                }
+                if (log2ss == 4) {
+                    emit(fminf(min3(mq[0], mq[1], mq[2]), mq[3]));
+                } else if (log2ss == 3) {
+                    emit(fminf(mq[0], mq[1]));
+                    emit(fminf(mq[2], mq[3]));
+                } else if (log2ss == 2) {
+                    emit(mq[0]);
+                    emit(mq[1]);
+                    emit(mq[2]);
+                    emit(mq[3]);
+                } else {
+                    acc = fminf(acc, fminf(min3(mq[0], mq[1], mq[2]), mq[3]));
+                    if (((j0 + jb + 16) & (ss - 1)) == 0) {
+                        emit(acc);
+                        acc = kInf;
+                    }
+                }
             }
         }
+        if (log2ss > 4 && (n & (ss - 1)) != 0 && ((((n + 15) & ~15)) & (ss - 1)) != 0) emit(acc);  // ragged last subgroup
         if (gleft != gsz) *grow = (unsigned short)((__float_as_uint(gmn) + 0xffffu) >> 16);  // ragged last group
     }
 
@@ -305,32 +344,34 @@ __global__ void __launch_bounds__(NWARPS * 32) knn_select_kernel(const float* __
     const int nq = min(32, m - q0);
     const bool resident = n <= KS_TILE;  // the single tile of pass 1 is still in shared memory
     for (int qi = 0; qi < nq; ++qi) {
-        const float tq = __shfl_sync(kFull, tau, qi);
+        // NaN and +inf never survive: the bound is clamped to the largest finite float
+        const float tq = fminf(__shfl_sync(kFull, tau, qi), 3.402823466e+38f);
         const float ax = __shfl_sync(kFull, qx, qi), ay = __shfl_sync(kFull, qy, qi), az = __shfl_sync(kFull, qz, qi);
-        // subgroups whose (rounded-down) minimum is <= tau, in ascending order
+        // subgroups whose (rounded-down) minimum is <= tau, in ascending order.  bf16 bit patterns of non-negative floats
+        // order like unsigned integers, and (v << 16) <= T  <=>  v <= (T >> 16); rows >= nsub hold 0xffff (never pass)
+        const unsigned tq16 = __float_as_uint(tq) >> 16;
+        const unsigned short* sp = &wsm->sub[lane][(qi + lane) & 31];  // sub[lane + 32 i][(qi + lane + 32 i) & 31]
         int npass = 0;
 #pragma unroll
         for (int i = 0; i < KS_NSUB / 32; ++i) {
-            const int sg = lane + 32 * i;
-            bool p = false;
-            if (sg < nsub) p = __uint_as_float((unsigned)wsm->sub[sg][(qi + sg) & 31] << 16) <= tq;
+            const bool p = (unsigned)sp[i * 32 * 32] <= tq16;
             const unsigned mask = __ballot_sync(kFull, p);
-            if (p) wsm->plist[npass + __popc(mask & lt)] = (unsigned short)sg;
+            if (p) wsm->sel.plist[npass + __popc(mask & lt)] = (unsigned short)(lane + 32 * i);
             npass += __popc(mask);
         }
         __syncwarp();
-        // rescan those subgroups: 4 consecutive candidates per lane, 128 per step.  Survivors are appended in ANY order
-        // (shared-memory counter): their 64-bit (d2, index) keys are unique, so the ranking below does not need them sorted.
+        // rescan those subgroups: 4 consecutive candidates per lane, 128 per step; survivors (d2 <= tau) are compacted
+        // with ballots into the key array (their 64-bit (d2, index) keys are unique, the ranking below orders them)
         const int total = npass << log2ss;
-        if (lane == 0) wsm->nsurv = 0;
-        __syncwarp();
+        int nsurv = 0;
         for (int p0 = 0; p0 < total; p0 += 128) {
             const int p = p0 + 4 * lane;
             const bool ok = p < total;
-            const int sg = wsm->plist[ok ? (p >> log2ss) : 0];
+            const int sg = wsm->sel.plist[ok ? (p >> log2ss) : 0];
             const int j = (sg << log2ss) + (p & (ss - 1));  // multiple of 4; j..j+3 stay inside the subgroup
+            const float tql = ok ? tq : -1.0f;              // lanes past the end of the list keep nothing
             float d[4];
-            if (resident) {
+            if (resident) {  // the tile is NaN-padded past n: a ragged last subgroup needs no index check
                 const float4 X = *reinterpret_cast<const float4*>(tile + j);
                 const float4 Y = *reinterpret_cast<const float4*>(tile + KS_TILE + j);
                 const float4 Z = *reinterpret_cast<const float4*>(tile + 2 * KS_TILE + j);
@@ -350,15 +391,14 @@ __global__ void __launch_bounds__(NWARPS * 32) knn_select_kernel(const float* __
             }
 #pragma unroll
             for (int u = 0; u < 4; ++u) {
-                // NaN and +inf never survive; j+u >= n: ragged last subgroup
-                if (ok && j + u < n && d[u] <= tq && d[u] < kInf) {
-                    const int pos = atomicAdd(&wsm->nsurv, 1);
-                    if (pos < KS_SCAP) wsm->key[pos] = ((unsigned long long)__float_as_uint(d[u]) << 32) | (unsigned)(j + u);
-                }
+                const bool keep = d[u] <= tql;  // false for NaN
+                const unsigned mk = __ballot_sync(kFull, keep);
+                const int pos = nsurv + __popc(mk & lt);
+                if (keep && pos < KS_SCAP) wsm->sel.key[pos] = ((unsigned long long)__float_as_uint(d[u]) << 32) | (unsigned)(j + u);
+                nsurv += __popc(mk);
             }
         }
         __syncwarp();
-        const int nsurv = wsm->nsurv;
         int* oi = idx + ((size_t)bz * m + q0 + qi) * k;
         float* od = dist2 ? dist2 + ((size_t)bz * m + q0 + qi) * k : nullptr;
         if (nsurv <= KS_SCAP) {
@@ -366,15 +406,15 @@ __global__ void __launch_bounds__(NWARPS * 32) knn_select_kernel(const float* __
             for (int e0 = 0; e0 < nsurv; e0 += 32) {
                 const int e = e0 + lane;
                 const bool have = e < nsurv;
-                const unsigned long long ke = have ? wsm->key[e] : ~0ull;
+                const unsigned long long ke = have ? wsm->sel.key[e] : ~0ull;
                 int rank = 0;
                 int f = 0;
                 for (; f + 2 <= nsurv; f += 2) {
-                    const ulonglong2 kf = *reinterpret_cast<const ulonglong2*>(wsm->key + f);
+                    const ulonglong2 kf = *reinterpret_cast<const ulonglong2*>(wsm->sel.key + f);
                     rank += (kf.x < ke) ? 1 : 0;
                     rank += (kf.y < ke) ? 1 : 0;
                 }
-                if (f < nsurv) rank += (wsm->key[f] < ke) ? 1 : 0;
+                if (f < nsurv) rank += (wsm->sel.key[f] < ke) ? 1 : 0;
                 if (have && rank < k) {
                     oi[rank] = (int)(unsigned)ke;
                     if (od) od[rank] = __uint_as_float((unsigned)(ke >> 32));
@@ -386,8 +426,8 @@ __global__ void __launch_bounds__(NWARPS * 32) knn_select_kernel(const float* __
             }
         } else if (lane == 0) {
             // survivor overflow: exact serial scan of every candidate for this query (the key array doubles as the list)
-            float* ldl = reinterpret_cast<float*>(wsm->key);
-            int* lil = reinterpret_cast<int*>(wsm->key) + KS_SCAP;
+            float* ldl = reinterpret_cast<float*>(wsm->sel.key);
+            int* lil = reinterpret_cast<int*>(wsm->sel.key) + KS_SCAP;
             for (int e = 0; e < k; ++e) {
                 ldl[e] = kInf;
                 lil[e] = 0;
@@ -428,7 +468,7 @@ static bool select_plan(int n, int k, int G, int* log2ss, int* gsz) {
     while (((n + (1 << l) - 1) >> l) > KS_NSUB) ++l;
     if ((1 << l) > KS_TILE) return false;
     const int nsub = (n + (1 << l) - 1) >> l;
-    for (int g = 4; g >= 1; g >>= 1) {
+    for (int g = 1; g <= 4; g <<= 1) {  // most groups first: the k-th smallest of more group minima is a tighter bound
         const int ng = (nsub + g - 1) / g;
         if (ng >= k && ng <= G) {
             *log2ss = l;
@@ -448,16 +488,26 @@ static int knn_dispatch(const float* xyz, const float* new_xyz, int b, int n, in
         case 4: return launch_smallk<4>(xyz, new_xyz, b, n, m, idx, dist2, st);
         default: break;
     }
-    // k <= 24 of 32 groups / k <= 48 of 64 groups keeps the expected survivor count (~G/(G-k) * k-ish) well under KS_SCAP
-    if (k <= 24 && select_plan(n, k, 32, &log2ss, &gsz)) {
-        // warps per CTA: as many as possible (they share the candidate tile) while the grid still covers the SMs --
-        // the training shapes have only 256..1024 queries per batch element
-        const long long want = 132;  // ~0.9 x SMs: one full wave of the widest CTA beats two waves of narrower ones
-        if ((long long)((m + 511) / 512) * b >= want) return launch_select<32, 16>(xyz, new_xyz, b, n, m, k, log2ss, gsz, idx, dist2, st);
-        if ((long long)((m + 255) / 256) * b >= want) return launch_select<32, 8>(xyz, new_xyz, b, n, m, k, log2ss, gsz, idx, dist2, st);
-        if ((long long)((m + 127) / 128) * b >= want) return launch_select<32, 4>(xyz, new_xyz, b, n, m, k, log2ss, gsz, idx, dist2, st);
-        return launch_select<32, 2>(xyz, new_xyz, b, n, m, k, log2ss, gsz, idx, dist2, st);
-    }
+    // Expected survivors of the bound "k-th smallest of G group minima": -ln(1 - k/G) * G, i.e. 31 for k = 20 of 32 groups
+    // but 24 of 64 groups (one ranking round instead of two, fewer subgroups to rescan); below k ~ 12 the two are equal
+    // and 32 groups cost less to sort.  k <= 24 of 32 / k <= 48 of 64 keeps the count well under KS_SCAP.
+    // Warps per CTA: as many as possible (they share the candidate tile) while the grid still covers the SMs -- the
+    // training shapes have only 256..1024 queries per batch element.
+    const long long want = 132;  // ~0.9 x SMs: one full wave of the widest CTA beats two waves of narrower ones
+    const int width = (long long)((m + 511) / 512) * b >= want ? 16 : (long long)((m + 255) / 256) * b >= want ? 8
+                    : (long long)((m + 127) / 128) * b >= want ? 4 : 2;
+#define PDGN_KS_LAUNCH(G_)                                                                                        \
+    do {                                                                                                          \
+        if (width == 16) return launch_select<G_, 16>(xyz, new_xyz, b, n, m, k, log2ss, gsz, idx, dist2, st);     \
+        if (width == 8) return launch_select<G_, 8>(xyz, new_xyz, b, n, m, k, log2ss, gsz, idx, dist2, st);       \
+        if (width == 4) return launch_select<G_, 4>(xyz, new_xyz, b, n, m, k, log2ss, gsz, idx, dist2, st);       \
+        return launch_select<G_, 2>(xyz, new_xyz, b, n, m, k, log2ss, gsz, idx, dist2, st);                       \
+    } while (0)
+    static const bool wide_groups = getenv("PDGN_KNN_G32") == nullptr;  // tuning hook: PDGN_KNN_G32=1 keeps 32 groups
+    if (k > 12 && k <= 24 && wide_groups && select_plan(n, k, 64, &log2ss, &gsz) && (n + (1 << log2ss) - 1) >> log2ss > 32 * gsz)
+        PDGN_KS_LAUNCH(64);
+    if (k <= 24 && select_plan(n, k, 32, &log2ss, &gsz)) PDGN_KS_LAUNCH(32);
+#undef PDGN_KS_LAUNCH
     if (k <= 48 && select_plan(n, k, 64, &log2ss, &gsz)) return launch_select<64, 8>(xyz, new_xyz, b, n, m, k, log2ss, gsz, idx, dist2, st);
     const size_t smem = (size_t)3 * KG_TILE * 4 + (size_t)k * KG_T * 8;
     PDGN_CUDA(cudaFuncSetAttribute(knn_generic_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
