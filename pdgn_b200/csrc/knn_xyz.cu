@@ -481,12 +481,16 @@ static bool select_plan(int n, int k, int G, int* log2ss, int* gsz) {
 
 static int knn_dispatch(const float* xyz, const float* new_xyz, int b, int n, int m, int k, int* idx, float* dist2, cudaStream_t st) {
     int log2ss = 0, gsz = 0;
-    switch (k) {  // tiny k: register-resident lists
-        case 1: return launch_smallk<1>(xyz, new_xyz, b, n, m, idx, dist2, st);
-        case 2: return launch_smallk<2>(xyz, new_xyz, b, n, m, idx, dist2, st);
-        case 3: return launch_smallk<3>(xyz, new_xyz, b, n, m, idx, dist2, st);
-        case 4: return launch_smallk<4>(xyz, new_xyz, b, n, m, idx, dist2, st);
-        default: break;
+    // tiny k with few candidates: register-resident lists (every lane inserts ~k ln(n) times, which keeps the whole warp in
+    // the divergent insertion path once n is in the hundreds: 22 instr/pair at n = 1024, so larger n goes to the select kernel)
+    static const bool force_smallk = getenv("PDGN_KNN_SMALLK") != nullptr;  // tuning hook
+    if (k <= 4 && (n < 256 || force_smallk || !select_plan(n, k, 32, &log2ss, &gsz))) {
+        switch (k) {
+            case 1: return launch_smallk<1>(xyz, new_xyz, b, n, m, idx, dist2, st);
+            case 2: return launch_smallk<2>(xyz, new_xyz, b, n, m, idx, dist2, st);
+            case 3: return launch_smallk<3>(xyz, new_xyz, b, n, m, idx, dist2, st);
+            default: return launch_smallk<4>(xyz, new_xyz, b, n, m, idx, dist2, st);
+        }
     }
     // Expected survivors of the bound "k-th smallest of G group minima": -ln(1 - k/G) * G, i.e. 31 for k = 20 of 32 groups
     // but 24 of 64 groups (one ranking round instead of two, fewer subgroups to rescan); below k ~ 12 the two are equal

@@ -21,3 +21,8 @@ for (b, n, k) in [(35, 2048, 20), (35, 1024, 20), (35, 512, 20), (35, 256, 20), 
     ms = t(lambda: ops.knn_xyz(k, xyz))
     print("b%d n%d k%d %.4f ms |" % (b, n, k, ms), end=" ")
 print()
+for (b, n, m) in [(35, 2048, 1024), (35, 1024, 512), (35, 512, 256)]:
+    unk = (torch.rand(b, n, 3, generator=g) * 2 - 1).to(dev)
+    kn = (torch.rand(b, m, 3, generator=g) * 2 - 1).to(dev)
+    print("nn3 b%d unknown%d known%d %.4f ms |" % (b, n, m, t(lambda: ops.nn3(unk, kn))), end=" ")
+print()
