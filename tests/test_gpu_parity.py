@@ -46,6 +46,20 @@ KNN_CASES = [
     ("U-n6000-k20", clouds_uniform, 1, 6000, 700, 20),
     ("S-16384-k32", clouds_sphere, 1, 16384, 1000, 32),
     ("T-ties-2048-k20", clouds_ties, 2, 2048, 600, 20),
+    # dispatch edges: 32- vs 64-group bound (k = 12 / 13 / 24), subgroup sizes 4 / 8 / 16 with ragged last blocks,
+    # small-k register kernel vs select kernel (n = 255 / 256), k <= 4 on ties
+    ("U-k12-G32", clouds_uniform, 2, 2048, 300, 12),
+    ("U-k13-G64", clouds_uniform, 2, 2048, 300, 13),
+    ("S-k24-G64", clouds_sphere, 2, 1500, 300, 24),
+    ("U-ss4-ragged", clouds_uniform, 2, 501, 130, 20),
+    ("U-ss8-ragged", clouds_uniform, 2, 1001, 130, 20),
+    ("U-ss16-ragged", clouds_uniform, 2, 2039, 130, 16),
+    ("U-k3-n255-smallk", clouds_uniform, 2, 255, 300, 3),
+    ("U-k3-n256-select", clouds_uniform, 2, 256, 300, 3),
+    ("T-k4-ties-select", clouds_ties, 2, 1024, 300, 4),
+    ("T-k2-ties-2048", clouds_ties, 1, 2048, 500, 2),
+    ("S-k1-2048", clouds_sphere, 2, 2048, 2048, 1),
+    ("U-k20-n70-G64-small", clouds_uniform, 2, 70, 50, 20),
 ]
 
 
