@@ -1,0 +1,24 @@
+"""Backward gather (pull) timings on the feature-sized shapes (tools/ only): grouping bwd and edge-feature bwd."""
+import sys
+import numpy as np
+import torch
+sys.path.insert(0, ".")
+import bench
+import os
+from pdgn_b200 import _lib, ops
+if os.environ.get('PDGN_LIB'):
+    _lib.SO_PATH = os.environ['PDGN_LIB']  # A/B against another build (tools only)
+    print('library:', _lib.SO_PATH)
+dev = torch.device("cuda:0")
+rng = np.random.default_rng(0)
+flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
+for (b, c, n, k) in [(35, 256, 1024, 10), (35, 128, 512, 10), (35, 64, 256, 10)]:
+    go = torch.randn(b, c, n, k, device=dev)
+    idx = torch.from_numpy(rng.integers(0, n, (b, n, k)).astype(np.int32)).to(dev)
+    ms = bench._time_ms(lambda: ops.group_bwd(go, idx, n), 10, flush)
+    gb = (go.numel() + idx.numel() + 2 * b * c * n) * 4 / 1e9
+    gee = torch.randn(b, 2 * c, n, k, device=dev)
+    idx64 = idx.long()
+    ms2 = bench._time_ms(lambda: ops.edge_feat_bwd(gee, idx64, c), 10, flush)
+    gb2 = (gee.numel() + 2 * b * c * n) * 4 / 1e9 + idx64.numel() * 8 / 1e9
+    print("B%d C%d N%d k%d: group_bwd %.1f us (%.0f GB/s)   edge_feat_bwd %.1f us (%.0f GB/s)" % (b, c, n, k, ms * 1e3, gb / ms * 1e3, ms2 * 1e3, gb2 / ms2 * 1e3), flush=True)
