@@ -9,7 +9,7 @@
 // matrix is never materialised because the cost is linear in the per-level weights: cost = sum_levels sum_kl w_kl*|p_k-q_l|.
 // HBM traffic per cloud pair: 49 KB in, 4 bytes out.
 //
-// Bound: FP32 issue + MUFU (one ex2 per point pair per sweep, one more rsqrt/sqrt in the cost sweep):
+// Bound: the MUFU pipe (one ex2 per point pair in the second sweep, one ex2 + one sqrt in the fused transport pass):
 // 27 sweeps x 2048^2 pairs x ~10 issue slots.  The arithmetic follows the reference statement by statement
 // (same d2 chain, level*d2 then __expf, same update formulas); sums are taken in a different order, so parity is by
 // tolerance (tests: 2e-4 relative against the recompiled reference kernels and the CPU oracle).
@@ -23,6 +23,11 @@ namespace pdgn {
 __device__ __forceinline__ float exp2_fast(float x) {
     float r;
     asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
+    return r;
+}
+__device__ __forceinline__ float mul_ftz(float a, float b) {
+    float r;
+    asm("mul.ftz.f32 %0, %1, %2;" : "=f"(r) : "f"(a), "f"(b));
     return r;
 }
 __device__ __forceinline__ float sqrt_fast(float x) {
@@ -142,15 +147,57 @@ __device__ __forceinline__ float box_gap2(const float4* a, const float4* b) {
     return dx * dx + dy * dy + dz * dz;
 }
 
+// One pass of a warp's own left points (4 rows per lane) over every right point: the transport sweep of level `l2a`
+//   w = exp(l2a*d2) * ratioL[k] * ratioR[l];  acc3[k] += w;  cost += w * |p_k - q_l|
+// fused (NEXT) with the first sweep of the NEXT level `l2b`, which walks the same point pairs
+//   acc1[k] += exp(l2b*d2) * remainR[l]
+// so that d2 is computed once and one sweep (and two CTA barriers) per level disappears.  Blocks of 32 right points whose
+// bounding box is farther from the warp's box than `reach2` (that of the coarser of the two levels) hold exact zeros only.
+template <bool NEXT>
+__device__ __forceinline__ void emd_transport_pass(const float4* __restrict__ Rr, const float* __restrict__ RemR, const float4* Wb,
+                                                   const float4* Rc, int nchR, int m, float reach2, float l2a, float l2b,
+                                                   const float (&ox)[EM_R], const float (&oy)[EM_R], const float (&oz)[EM_R],
+                                                   const float (&ratL)[EM_R], float (&acc3)[EM_R], float (&acc1)[EM_R],
+                                                   float& cost) {
+    for (int c = 0; c < nchR; ++c) {
+        if (box_gap2(Wb, Rc + 2 * c) > reach2) continue;
+        const int le = min(m, (c + 1) * EM_CH);
+#pragma unroll 2
+        for (int l = c * EM_CH; l < le; ++l) {
+            const float4 q = Rr[l];
+            const float rr = NEXT ? RemR[l] : 0.f;
+#pragma unroll
+            for (int i = 0; i < EM_R; ++i) {
+                const float d2 = d2_xyz(q.x, q.y, q.z, ox[i], oy[i], oz[i]);
+                float e3;
+                if (NEXT) {
+                    // the levels are a factor 4 apart (l2a == 4*l2b exactly), so exp(l2a*d2) = exp(l2b*d2)^4: two multiplies
+                    // instead of a second MUFU.EX2 (the kernel is MUFU bound); mul.ftz keeps the underflow-to-zero of ex2.ftz
+                    const float e1 = exp2_fast(l2b * d2);
+                    acc1[i] = __fmaf_rn(e1, rr, acc1[i]);
+                    const float e2 = mul_ftz(e1, e1);
+                    e3 = mul_ftz(e2, e2);
+                } else {
+                    e3 = exp2_fast(l2a * d2);
+                }
+                const float w = e3 * ratL[i] * q.w;
+                acc3[i] += w;
+                cost = __fmaf_rn(w, sqrt_fast(d2), cost);
+            }
+        }
+    }
+}
+
 __global__ void __launch_bounds__(EM_T, 2)
 emd_allpairs_kernel(const float* __restrict__ A, const float* __restrict__ B, int ncols, int n, int m, int rstrip,
                     float* __restrict__ out, long long ld_out) {
     extern __shared__ __align__(16) float4 em_sm[];
     float4* L = em_sm;                 // [EM_MAX] left cloud:  x, y, z, ratioL
-    float4* Rr = em_sm + EM_MAX;       // [EM_MAX] right cloud: x, y, z, remainR (sweep 1) / ratioR (sweep 3)
+    float4* Rr = em_sm + EM_MAX;       // [EM_MAX] right cloud: x, y, z, ratioR
     float4* Lc = em_sm + 2 * EM_MAX;   // [2*EM_NCH] chunk boxes of the left cloud: (lo, hi) pairs
     float4* Rc = Lc + 2 * EM_NCH;      // [2*EM_NCH] chunk boxes of the right cloud
     float4* Wb = Rc + 2 * EM_NCH + 4 * (threadIdx.x >> 5);  // this warp's own boxes: left (lo, hi), right (lo, hi)
+    float* RemR = reinterpret_cast<float*>(Rc + 2 * EM_NCH + 4 * (EM_T / 32));  // [EM_MAX] remainR of the right cloud
     __shared__ float red[EM_T / 32];
     const int t = threadIdx.x, lane = t & 31, warp = t >> 5;
     const int s = blockIdx.y;
@@ -161,12 +208,14 @@ emd_allpairs_kernel(const float* __restrict__ A, const float* __restrict__ B, in
 
     const float* Ap = A + (size_t)s * n * 3;
     EmBox ownL{kInf, kInf, kInf, -kInf, -kInf, -kInf};  // box of the warp's own left points
+    float ox[EM_R], oy[EM_R], oz[EM_R];                 // own left points (registers for the whole strip)
 #pragma unroll
     for (int i = 0; i < EM_R; ++i) {
         const int p = own0 + 32 * i;
         float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
         if (p < n) { v.x = Ap[p * 3]; v.y = Ap[p * 3 + 1]; v.z = Ap[p * 3 + 2]; }
         L[p] = v;
+        ox[i] = v.x; oy[i] = v.y; oz[i] = v.z;
         const EmBox bx = warp_box(v.x, v.y, v.z, p < n);
         if (lane == 0) {
             Lc[2 * (warp * EM_R + i)] = make_float4(bx.lx, bx.ly, bx.lz, 0.f);
@@ -175,6 +224,10 @@ emd_allpairs_kernel(const float* __restrict__ A, const float* __restrict__ B, in
         box_join(ownL, bx);
     }
     if (lane == 0) { Wb[0] = make_float4(ownL.lx, ownL.ly, ownL.lz, 0.f); Wb[1] = make_float4(ownL.hx, ownL.hy, ownL.hz, 0.f); }
+    // ex2.approx.ftz(l2*d2) is exactly +0 once l2*d2 <= -127; blocks whose boxes are farther apart than sqrt(reach2) (one
+    // more unit of margin) contribute exact zeros and are skipped
+    auto reach2_of = [](float l2) { return (128.0f / -l2) * 1.0002f; };
+    constexpr float kLog2e = 1.4426950408889634f;
     for (int r = r_begin; r < r_end; ++r) {
         const float* Bp = B + (size_t)r * m * 3;
         __syncthreads();  // previous pair fully consumed
@@ -185,9 +238,10 @@ emd_allpairs_kernel(const float* __restrict__ A, const float* __restrict__ B, in
             const int p = own0 + 32 * i;
             remL[i] = p < n ? multiL : 0.f;
             remR[i] = p < m ? multiR : 0.f;
-            float4 v = make_float4(0.f, 0.f, 0.f, remR[i]);
+            float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
             if (p < m) { v.x = Bp[p * 3]; v.y = Bp[p * 3 + 1]; v.z = Bp[p * 3 + 2]; }
             Rr[p] = v;
+            RemR[p] = remR[i];
             const EmBox bx = warp_box(v.x, v.y, v.z, p < m);
             if (lane == 0) {
                 Rc[2 * (warp * EM_R + i)] = make_float4(bx.lx, bx.ly, bx.lz, 0.f);
@@ -199,43 +253,42 @@ emd_allpairs_kernel(const float* __restrict__ A, const float* __restrict__ B, in
         __syncthreads();
         float cost = 0.f;
         float level = -16384.f;  // -4^7, then /4 per level down to -4^-1
-        for (int j = 7; j > -2; --j, level *= 0.25f) {
-            const float l2 = level * 1.4426950408889634f;  // level * log2(e)
-            // ex2.approx.ftz(l2*d2) is exactly +0 once l2*d2 <= -127; blocks whose boxes are farther apart than sqrt(reach2)
-            // (one more unit of margin) contribute exact zeros and are skipped
-            const float reach2 = (128.0f / -l2) * 1.0002f;
-            float ox[EM_R], oy[EM_R], oz[EM_R], acc[EM_R];
-            // ---- sweep 1: ratioL[k] = remainL[k] / (1e-9 + sum_l exp(level*d2) * remainR[l])
+        // ---- first sweep of the first level: ratioL[k] = remainL[k] / (1e-9 + sum_l exp(level*d2) * remainR[l])
+        {
+            const float l2 = level * kLog2e, reach2 = reach2_of(l2);
+            float acc[EM_R];
 #pragma unroll
-            for (int i = 0; i < EM_R; ++i) {
-                const float4 v = L[own0 + 32 * i];
-                ox[i] = v.x; oy[i] = v.y; oz[i] = v.z;
-                acc[i] = 1e-9f;
-            }
-                for (int c = 0; c < nchR; ++c) {
-                    if (box_gap2(Wb, Rc + 2 * c) > reach2) continue;
-                    const int le = min(m, (c + 1) * EM_CH);
+            for (int i = 0; i < EM_R; ++i) acc[i] = 1e-9f;
+            for (int c = 0; c < nchR; ++c) {
+                if (box_gap2(Wb, Rc + 2 * c) > reach2) continue;
+                const int le = min(m, (c + 1) * EM_CH);
 #pragma unroll 2
-                    for (int l = c * EM_CH; l < le; ++l) {
-                        const float4 q = Rr[l];
+                for (int l = c * EM_CH; l < le; ++l) {
+                    const float4 q = Rr[l];
+                    const float rr = RemR[l];
 #pragma unroll
-                        for (int i = 0; i < EM_R; ++i)
-                            acc[i] = __fmaf_rn(exp2_fast(l2 * d2_xyz(q.x, q.y, q.z, ox[i], oy[i], oz[i])), q.w, acc[i]);
-                    }
+                    for (int i = 0; i < EM_R; ++i)
+                        acc[i] = __fmaf_rn(exp2_fast(l2 * d2_xyz(q.x, q.y, q.z, ox[i], oy[i], oz[i])), rr, acc[i]);
                 }
+            }
 #pragma unroll
             for (int i = 0; i < EM_R; ++i) {
                 ratL[i] = remL[i] / acc[i];
                 L[own0 + 32 * i].w = ratL[i];
             }
-            __syncthreads();
-            // ---- sweep 2: sumr[l] = remainR[l] * sum_k exp(level*d2) * ratioL[k]; consumption; ratioR; remainR
+        }
+        for (int j = 7; j > -2; --j, level *= 0.25f) {
+            const float l2 = level * kLog2e, reach2 = reach2_of(l2);
+            __syncthreads();  // ratioL of this level is in L[].w
+            // ---- second sweep: sumr[l] = remainR[l] * sum_k exp(level*d2) * ratioL[k]; consumption; ratioR; remainR
+            {
+                float px[EM_R], py[EM_R], pz[EM_R], acc[EM_R];
 #pragma unroll
-            for (int i = 0; i < EM_R; ++i) {
-                const float4 v = Rr[own0 + 32 * i];
-                ox[i] = v.x; oy[i] = v.y; oz[i] = v.z;
-                acc[i] = 0.f;
-            }
+                for (int i = 0; i < EM_R; ++i) {
+                    const float4 v = Rr[own0 + 32 * i];
+                    px[i] = v.x; py[i] = v.y; pz[i] = v.z;
+                    acc[i] = 0.f;
+                }
                 for (int c = 0; c < nchL; ++c) {
                     if (box_gap2(Wb + 2, Lc + 2 * c) > reach2) continue;
                     const int ke = min(n, (c + 1) * EM_CH);
@@ -244,46 +297,36 @@ emd_allpairs_kernel(const float* __restrict__ A, const float* __restrict__ B, in
                         const float4 p = L[k];
 #pragma unroll
                         for (int i = 0; i < EM_R; ++i)
-                            acc[i] = __fmaf_rn(exp2_fast(l2 * d2_xyz(ox[i], oy[i], oz[i], p.x, p.y, p.z)), p.w, acc[i]);
+                            acc[i] = __fmaf_rn(exp2_fast(l2 * d2_xyz(px[i], py[i], pz[i], p.x, p.y, p.z)), p.w, acc[i]);
                     }
                 }
+                // (own entries only: nobody else reads ratioR / remainR before the barrier below)
 #pragma unroll
-            for (int i = 0; i < EM_R; ++i) {
-                const float sumr = acc[i] * remR[i];
-                const float consumption = fminf(remR[i] / (sumr + 1e-9f), 1.0f);
-                Rr[own0 + 32 * i].w = consumption * remR[i];  // ratioR
-                remR[i] = fmaxf(0.0f, remR[i] - sumr);
-            }
-            __syncthreads();
-            // ---- sweep 3: w = exp(level*d2)*ratioL[k]*ratioR[l]; remainL[k] -= sum_l w; cost += w*|p_k - q_l|
-#pragma unroll
-            for (int i = 0; i < EM_R; ++i) {
-                const float4 v = L[own0 + 32 * i];
-                ox[i] = v.x; oy[i] = v.y; oz[i] = v.z;
-                acc[i] = 0.f;
-            }
-                for (int c = 0; c < nchR; ++c) {
-                    if (box_gap2(Wb, Rc + 2 * c) > reach2) continue;
-                    const int le = min(m, (c + 1) * EM_CH);
-#pragma unroll 2
-                    for (int l = c * EM_CH; l < le; ++l) {
-                        const float4 q = Rr[l];
-#pragma unroll
-                        for (int i = 0; i < EM_R; ++i) {
-                            const float d2 = d2_xyz(q.x, q.y, q.z, ox[i], oy[i], oz[i]);
-                            const float w = exp2_fast(l2 * d2) * ratL[i] * q.w;
-                            acc[i] += w;
-                            cost = __fmaf_rn(w, sqrt_fast(d2), cost);
-                        }
-                    }
+                for (int i = 0; i < EM_R; ++i) {
+                    const float sumr = acc[i] * remR[i];
+                    const float consumption = fminf(remR[i] / (sumr + 1e-9f), 1.0f);
+                    Rr[own0 + 32 * i].w = consumption * remR[i];  // ratioR
+                    remR[i] = fmaxf(0.0f, remR[i] - sumr);
+                    RemR[own0 + 32 * i] = remR[i];
                 }
-            __syncthreads();  // everyone is done reading ratioR before remainR goes back into the .w slots
+            }
+            __syncthreads();  // ratioR and the new remainR are in shared memory
+            // ---- transport sweep of this level fused with the first sweep of the next one
+            float acc3[EM_R], acc1[EM_R];
+#pragma unroll
+            for (int i = 0; i < EM_R; ++i) { acc3[i] = 0.f; acc1[i] = 1e-9f; }
+            if (j > -1) {
+                const float l2n = level * 0.25f * kLog2e;
+                emd_transport_pass<true>(Rr, RemR, Wb, Rc, nchR, m, reach2_of(l2n), l2, l2n, ox, oy, oz, ratL, acc3, acc1, cost);
+            } else {
+                emd_transport_pass<false>(Rr, RemR, Wb, Rc, nchR, m, reach2, l2, 0.f, ox, oy, oz, ratL, acc3, acc1, cost);
+            }
 #pragma unroll
             for (int i = 0; i < EM_R; ++i) {
-                remL[i] = fmaxf(0.0f, remL[i] - acc[i]);
-                Rr[own0 + 32 * i].w = remR[i];
+                remL[i] = fmaxf(0.0f, remL[i] - acc3[i]);
+                ratL[i] = remL[i] / acc1[i];
+                L[own0 + 32 * i].w = ratL[i];  // read by the next level's second sweep (after its barrier)
             }
-            __syncthreads();
         }
         cost = warp_sum(cost);
         if (lane == 0) red[warp] = cost;
@@ -324,7 +367,7 @@ extern "C" int pdgn_emd_allpairs(const float* A, const float* B, int na, int nb,
     PDGN_CHECK_LAUNCH();
     emd_sort_kernel<<<ncols, EM_SORT_T, 0, st>>>(B, col0, m, SB);
     PDGN_CHECK_LAUNCH();
-    const size_t smem = (size_t)(2 * EM_MAX + 4 * EM_NCH + 4 * (EM_T / 32)) * sizeof(float4);
+    const size_t smem = (size_t)(2 * EM_MAX + 4 * EM_NCH + 4 * (EM_T / 32)) * sizeof(float4) + (size_t)EM_MAX * sizeof(float);
     PDGN_CUDA(cudaFuncSetAttribute(emd_allpairs_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     int sms = 148, dev = 0;
     if (cudaGetDevice(&dev) == cudaSuccess) cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
