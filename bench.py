@@ -136,7 +136,7 @@ def run_reference(args, rank):
     """--impl reference: the reference's CPU path on the host cores (rank 0 only)."""
     if rank != 0:
         return
-    n_s, n_r = 2, 50  # 100 cloud pairs per step (~3 s on 8 cores): bounded sample of the 1000x1000 workload
+    n_s, n_r = 8, 50  # 400 cloud pairs per step (~3.5 s on 16 cores): bounded sample of the 1000x1000 workload
     for _ in range(args.warmup):
         cpu_reference_rate(1, 10)
     rates, times = [], []
@@ -317,7 +317,7 @@ def main():
         line["gathers"] = bench_gathers(dev, float(peaks.get("hbm_gbs") or 6650.0), "measured" if peaks.get("hbm_gbs") else "fallback")
         line["emd"] = bench_emd(dev)
         if world == 1:
-            n_s, n_r = 4, 50
+            n_s, n_r = 24, 50  # ~10 s of host work: a bounded sample of the 1000 x 1000 workload
             rate, dt = cpu_reference_rate(n_s, n_r)
             line["cpu_baseline"] = {"value": rate, "unit": UNIT, "cores": os.cpu_count() or 1, "kind": "port", "seconds": dt,
                                     "sample": "%d x %d cloud pairs of 2048 points (reference Gram-form distChamfer loop, batch_size 50)" % (n_s, n_r)}
