@@ -34,13 +34,20 @@ __device__ __forceinline__ float sqdist(const float (&q)[D], const float (&p)[D]
 }
 
 // x [b,nx,D] queries, y [b,ny,D] candidates -> mind [b,nx], argm [b,nx] (argm may be null)
-template <int D>
-__global__ void __launch_bounds__(CH_T) nn_min_kernel(const float* __restrict__ x, const float* __restrict__ y, int nx, int ny,
-                                                     float* __restrict__ mind, int* __restrict__ argm) {
+// S "slices" of CH_T threads share the queries of a CTA: slice s scans the candidate quads s, s+S, s+2S, ... of every tile
+// and the S partial (minimum, index) pairs of a query are merged lexicographically at the end (lowest index among equal
+// minima, exactly what a single in-order scan gives).  The training shapes have only a few hundred queries per batch
+// element: with S = 1 they put one warp on each scheduler (27 us for 35 x 1024 x 1024, 21 % of the issue roofline).
+template <int D, int S>
+__global__ void __launch_bounds__(CH_T * S) nn_min_kernel(const float* __restrict__ x, const float* __restrict__ y, int nx, int ny,
+                                                         float* __restrict__ mind, int* __restrict__ argm) {
     constexpr int CH_TILE = ChTile<D>::value;
-    __shared__ __align__(16) float tile[D * CH_TILE];
+    constexpr int MERGE = S > 1 ? 2 * S * CH_T * CH_Q : 0;          // floats needed to merge the slices
+    constexpr int SMEM = D * CH_TILE > MERGE ? D * CH_TILE : MERGE;
+    __shared__ __align__(16) float tile[SMEM];
     const int bz = blockIdx.y;
-    const int q0 = (blockIdx.x * CH_T + threadIdx.x) * CH_Q;
+    const int qt = threadIdx.x % CH_T, slice = threadIdx.x / CH_T;  // slice is warp-uniform (CH_T is a multiple of 32)
+    const int q0 = (blockIdx.x * CH_T + qt) * CH_Q;
     float q[CH_Q][D];
     float best[CH_Q];
     int besti[CH_Q];
@@ -58,13 +65,13 @@ __global__ void __launch_bounds__(CH_T) nn_min_kernel(const float* __restrict__ 
         const int cnt4 = (cnt + 3) & ~3;
         __syncthreads();
         // AoS global -> SoA shared (coalesced global reads); pad the tail quad with the tile's first candidate
-        for (int e = threadIdx.x; e < cnt4 * D; e += CH_T) {
+        for (int e = threadIdx.x; e < cnt4 * D; e += CH_T * S) {
             const int j = e / D, c = e - j * D;
             tile[c * CH_TILE + j] = yb[(size_t)(j0 + (j < cnt ? j : 0)) * D + c];
         }
         __syncthreads();
 #pragma unroll 1
-        for (int j = 0; j < cnt4; j += 4) {
+        for (int j = 4 * slice; j < cnt4; j += 4 * S) {
             float4 P[D];
 #pragma unroll
             for (int c = 0; c < D; ++c) P[c] = *reinterpret_cast<const float4*>(tile + c * CH_TILE + j);
@@ -76,13 +83,38 @@ __global__ void __launch_bounds__(CH_T) nn_min_kernel(const float* __restrict__ 
 #pragma unroll
                 for (int r = 0; r < CH_Q; ++r) {
                     const float d = sqdist<D>(q[r], p);
-                    if (d < best[r]) {  // padded duplicates can never be strictly smaller than their original
+                    // a padded duplicate is never strictly smaller than its original within a slice, and across slices the
+                    // original wins the merge with its lower index
+                    if (d < best[r]) {
                         best[r] = d;
                         besti[r] = j0 + j + u;
                     }
                 }
             }
         }
+    }
+    if (S > 1) {
+        __syncthreads();  // the last tile is consumed: its storage becomes the merge buffer
+        float* sb = tile;                                        // [S][CH_T*CH_Q]
+        int* si = reinterpret_cast<int*>(tile + S * CH_T * CH_Q);  // [S][CH_T*CH_Q]
+#pragma unroll
+        for (int r = 0; r < CH_Q; ++r) {
+            sb[slice * CH_T * CH_Q + r * CH_T + qt] = best[r];
+            si[slice * CH_T * CH_Q + r * CH_T + qt] = besti[r];
+        }
+        __syncthreads();
+        if (slice != 0) return;
+#pragma unroll
+        for (int r = 0; r < CH_Q; ++r)
+#pragma unroll
+            for (int o = 1; o < S; ++o) {
+                const float d = sb[o * CH_T * CH_Q + r * CH_T + qt];
+                const int i = si[o * CH_T * CH_Q + r * CH_T + qt];
+                if (d < best[r] || (d == best[r] && i < besti[r])) {
+                    best[r] = d;
+                    besti[r] = i;
+                }
+            }
     }
 #pragma unroll
     for (int r = 0; r < CH_Q; ++r)
@@ -115,7 +147,24 @@ __global__ void __launch_bounds__(256) chamfer_bwd_kernel(const float* __restric
 template <int D>
 static int launch_nn_min(const float* x, const float* y, int b, int nx, int ny, float* mind, int* argm, cudaStream_t st) {
     dim3 grid((nx + CH_T * CH_Q - 1) / (CH_T * CH_Q), b);
-    nn_min_kernel<D><<<grid, CH_T, 0, st>>>(x, y, nx, ny, mind, argm);
+    // slices per CTA: enough warps to give every scheduler of the chip ~4, but at least 16 candidate quads per slice
+    static const int sms = [] {
+        int dev = 0, v = 148;
+        if (cudaGetDevice(&dev) != cudaSuccess || cudaDeviceGetAttribute(&v, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || v <= 0) v = 148;
+        return v;
+    }();
+    const long long ctas = (long long)grid.x * grid.y;
+    constexpr int kMaxSlices = D <= 8 ? 8 : 4;  // 1024 threads leave 64 registers: not enough for D > 8 channels
+    int slices = 1;
+    while (slices < kMaxSlices && ctas * (CH_T / 32) * slices < 16LL * sms && ny >= 64 * (2 * slices)) slices <<= 1;
+    switch (slices) {
+        case 8:
+            if constexpr (kMaxSlices >= 8) nn_min_kernel<D, 8><<<grid, CH_T * 8, 0, st>>>(x, y, nx, ny, mind, argm);
+            break;
+        case 4: nn_min_kernel<D, 4><<<grid, CH_T * 4, 0, st>>>(x, y, nx, ny, mind, argm); break;
+        case 2: nn_min_kernel<D, 2><<<grid, CH_T * 2, 0, st>>>(x, y, nx, ny, mind, argm); break;
+        default: nn_min_kernel<D, 1><<<grid, CH_T, 0, st>>>(x, y, nx, ny, mind, argm); break;
+    }
     PDGN_CHECK_LAUNCH();
     return PDGN_OK;
 }
