@@ -134,6 +134,20 @@ int pdgn_local_stats_fwd(const float *xyz, const int *idx, int b, int n, int m, 
 int pdgn_local_stats_bwd(const float *xyz, const int *idx, const float *mu, const float *grad_mu, const float *grad_cov,
                          int b, int n, int m, int k, float *grad_xyz, void *stream);
 
+/* ---- the whole loss side of get_local_pair in one call (next row) ---------------------------------------------
+ * Replaces get_local_pair (models/PDGNet_v2.py:136-155): Gen_QueryAndGroupXYZ on (pt1, pt1) and (pt2, pt1)
+ * (lib/pointops/functions/pointops.py:670-703), compute_mean_covariance (:127-134) and the two ChamferLoss calls
+ * (utils/chamfer_loss.py:13-38) divided by M.  pt1 [b,3,m], pt2 [b,3,n] (channel-first, as the generator emits them) ->
+ * out[0] = like_mu12, out[1] = like_var12 (device scalars).  Every intermediate (transposed clouds, kNN indices,
+ * statistics, arg-minima) stays in `workspace` (pdgn_local_pair_workspace(b,m,n,k) bytes, 16-byte aligned), which the
+ * backward call reuses: grad_pt1 [b,3,m] and grad_pt2 [b,3,n] are ADDED into, grad_out[2] holds the upstream gradients
+ * of the two scalars (device).  1 <= k <= 64; m, n >= 1. */
+size_t pdgn_local_pair_workspace(int b, int m, int n, int k);
+int pdgn_local_pair_fwd(const float *pt1, const float *pt2, int b, int m, int n, int k, float *out, void *workspace,
+                        size_t workspace_bytes, void *stream);
+int pdgn_local_pair_bwd(int b, int m, int n, int k, const float *grad_out, float *grad_pt1, float *grad_pt2,
+                        void *workspace, size_t workspace_bytes, void *stream);
+
 /* ---- feature-space kNN of the generator ---------------------------------------------------------------
  * Replaces bmm + torch.sort + slice in get_edge_features{,_xyz} (models/PDGNet_v2.py:449-459, :492-502).
  * x [b,c,n] -> idx int64 [b,n,k]: ranks skip..skip+k-1 of the ascending (d2, index) order of exact FP32

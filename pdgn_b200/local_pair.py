@@ -1,5 +1,5 @@
 """Fused loss-side of PDGN's shape-preserving loss: get_local_pair (models/PDGNet_v2.py:136-155) in ~12 launches
-instead of ~45 (next row SURVEY.md 8f-2).
+instead of ~45, enqueued by ONE C call per direction (next row SURVEY.md 8f-2).
 
     like_mu12, like_var12 = get_local_pair(pt1 [B,3,M], pt2 [B,3,N])
 
@@ -8,10 +8,13 @@ Same value and gradients as the reference composition
 but the [B,3,M,k] grouped tensors, their transposes and the dense mean/repeat/bmm chain never exist: kNN indices feed
 pdgn_local_stats_fwd directly.  `pdgn_b200.dropin.install()` rebinds PDGNet_v2.get_local_pair to this function.
 """
+import os
+
 import torch
 from torch.autograd import Function
 
 from . import ops
+from ._lib import check, lib
 from .chamfer_loss import chamfer_min
 
 
@@ -35,8 +38,50 @@ class _LocalStats(Function):
 local_stats = _LocalStats.apply
 
 
+class _LocalPairCall(Function):
+    """The whole chain behind one C call per direction (csrc/local_pair.cu): no torch op between the kernels."""
+
+    @staticmethod
+    def forward(ctx, pt1, pt2, k):
+        pt1, pt2 = pt1.contiguous(), pt2.contiguous()
+        b, _, m = pt1.shape
+        n = pt2.shape[2]
+        L = lib()
+        ws_bytes = L.pdgn_local_pair_workspace(b, m, n, k)
+        ws = torch.empty((ws_bytes,), dtype=torch.uint8, device=pt1.device)
+        out = torch.empty((2,), dtype=torch.float32, device=pt1.device)
+        with torch.cuda.device(pt1.device):
+            check(L.pdgn_local_pair_fwd(pt1.data_ptr(), pt2.data_ptr(), b, m, n, k, out.data_ptr(), ws.data_ptr(), ws_bytes,
+                                        torch.cuda.current_stream(pt1.device).cuda_stream), "pdgn_local_pair_fwd")
+        ctx.ws, ctx.dims = ws, (b, m, n, k)
+        return out.unbind(0)
+
+    @staticmethod
+    def backward(ctx, g_mu, g_var):
+        b, m, n, k = ctx.dims
+        ws = ctx.ws
+        gout = torch.stack([g_mu, g_var]).to(torch.float32).contiguous()
+        gp1 = torch.zeros((b, 3, m), dtype=torch.float32, device=ws.device)
+        gp2 = torch.zeros((b, 3, n), dtype=torch.float32, device=ws.device)
+        with torch.cuda.device(ws.device):
+            check(lib().pdgn_local_pair_bwd(b, m, n, k, gout.data_ptr(), gp1.data_ptr(), gp2.data_ptr(), ws.data_ptr(), ws.numel(),
+                                            torch.cuda.current_stream(ws.device).cuda_stream), "pdgn_local_pair_bwd")
+        return gp1, gp2, None
+
+
 def get_local_pair(pt1, pt2, nsample=20):
-    """pt1 [B,3,M], pt2 [B,3,N] -> (like_mu12, like_var12), 0-d tensors (PDGNet_v2.py:136-155)."""
+    """pt1 [B,3,M], pt2 [B,3,N] -> (like_mu12, like_var12), 0-d tensors (PDGNet_v2.py:136-155).
+
+    One C call forward, one backward (PDGN_B200_LOCAL_PAIR=ops selects the op-by-op composition below, same kernels)."""
+    if os.environ.get("PDGN_B200_LOCAL_PAIR", "call") != "ops" and nsample <= 64:
+        if pt1.dtype != torch.float32 or pt2.dtype != torch.float32 or not pt1.is_cuda or not pt2.is_cuda:
+            raise TypeError("get_local_pair takes CUDA float32 tensors [B,3,M] / [B,3,N]")
+        return _LocalPairCall.apply(pt1, pt2, int(nsample))
+    return get_local_pair_ops(pt1, pt2, nsample)
+
+
+def get_local_pair_ops(pt1, pt2, nsample=20):
+    """The same chain composed from the individual ops (autograd through _LocalStats and chamfer_min)."""
     m = pt1.size(2)
     p1 = pt1.transpose(1, 2).contiguous()           # [B,M,3]; also the query set (new_xyz)
     p2 = pt2.transpose(1, 2).contiguous()

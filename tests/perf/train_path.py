@@ -91,11 +91,12 @@ t_ref_f = ev_time(lambda: loss_side(RefGroup(), RefChamfer(), False), reps=2, wa
 from pdgn_b200 import local_pair as fused  # noqa: E402
 
 
-def loss_side_fused(backward):
+def loss_side_fused(backward, fn=None):
+    fn = fn or fused.get_local_pair
     leaves = {n: p.clone().requires_grad_(backward) for n, p in pts.items()}
     total = 0
     for m_, n_ in sizes:
-        a, b = fused.get_local_pair(leaves[m_], leaves[n_])
+        a, b = fn(leaves[m_], leaves[n_])
         total = total + a + b
     if backward:
         total.backward()
@@ -104,8 +105,11 @@ def loss_side_fused(backward):
 
 t_fused = ev_time(lambda: loss_side_fused(True))
 t_fused_f = ev_time(lambda: loss_side_fused(False))
+t_fops = ev_time(lambda: loss_side_fused(True, fused.get_local_pair_ops))
+t_fops_f = ev_time(lambda: loss_side_fused(False, fused.get_local_pair_ops))
 print("loss side, 6 x get_local_pair (12 kNN+group, 12 Chamfer), B=35:")
-print("  pdgn_b200 fused get_local_pair  fwd+bwd %8.3f ms   fwd %8.3f ms" % (t_fused, t_fused_f))
+print("  pdgn_b200 get_local_pair, one C call per direction  fwd+bwd %8.3f ms   fwd %8.3f ms" % (t_fused, t_fused_f))
+print("  pdgn_b200 get_local_pair, fused ops from Python     fwd+bwd %8.3f ms   fwd %8.3f ms" % (t_fops, t_fops_f))
 print("  pdgn_b200 op-by-op composition  fwd+bwd %8.3f ms   fwd %8.3f ms" % (t_ours, t_ours_f))
 print("  reference kernels + torch Gram Chamfer on this GPU, fwd only %8.3f ms" % t_ref_f)
 

@@ -604,6 +604,34 @@ def test_fused_get_local_pair_matches_reference_composition(dev, b, m, n):
     torch.testing.assert_close(a2.grad, b2.grad, rtol=2e-3, atol=2e-5)
 
 
+@pytest.mark.parametrize("b,m,n,k", [(3, 256, 512, 20), (2, 1024, 2048, 20), (2, 100, 77, 8), (1, 33, 500, 20)])
+def test_single_call_local_pair_equals_op_composition(dev, b, m, n, k):
+    """pdgn_local_pair_fwd/bwd (one C call per direction) against the same kernels composed op by op in Python: the values
+    differ only by the order of the two final sums, the gradients by the atomics' order."""
+    from pdgn_b200 import local_pair
+    rng = np.random.default_rng(b * 1000 + m + n)
+    p1 = G(np.ascontiguousarray(clouds_sphere(rng, b, m, 3).transpose(0, 2, 1)), dev)
+    p2 = G(np.ascontiguousarray(clouds_uniform(rng, b, n, 3).transpose(0, 2, 1)), dev)
+    a1, a2 = p1.clone().requires_grad_(True), p2.clone().requires_grad_(True)
+    b1, b2 = p1.clone().requires_grad_(True), p2.clone().requires_grad_(True)
+    mu_c, var_c = local_pair.get_local_pair(a1, a2, k)
+    mu_o, var_o = local_pair.get_local_pair_ops(b1, b2, k)
+    assert mu_c.shape == () and var_c.shape == ()
+    torch.testing.assert_close(mu_c, mu_o, rtol=2e-6, atol=0)
+    torch.testing.assert_close(var_c, var_o, rtol=2e-6, atol=0)
+    (2.0 * mu_c - 0.5 * var_c).backward()
+    (2.0 * mu_o - 0.5 * var_o).backward()
+    torch.testing.assert_close(a1.grad, b1.grad, rtol=1e-4, atol=1e-7)
+    torch.testing.assert_close(a2.grad, b2.grad, rtol=1e-4, atol=1e-7)
+    # only one of the two outputs used: the other one's upstream gradient is zero
+    c1 = p1.clone().requires_grad_(True)
+    mu_only, _ = local_pair.get_local_pair(c1, p2, k)
+    mu_only.backward()
+    d1 = p1.clone().requires_grad_(True)
+    local_pair.get_local_pair_ops(d1, p2, k)[0].backward()
+    torch.testing.assert_close(c1.grad, d1.grad, rtol=1e-4, atol=1e-7)
+
+
 def test_local_stats_against_numpy(dev):
     from oracle import cpu as ocpu
     from pdgn_b200 import ops
