@@ -220,33 +220,38 @@ struct KsSelect {                      // scratch of the query being selected (p
                                        //   key == the reference's (d2, index) order
     unsigned short plist[KS_NSUB];     // subgroups that may hold survivors
 };
-template <int G>
+template <int G, int S>
 struct alignas(16) KsWarp {
     unsigned short sub[KS_NSUB][32];   // [subgroup][(query + subgroup) & 31]  bf16, rounded down  (swizzled: both the
                                        //   lane=query writes and the lane=subgroup reads are bank-conflict free)
     union {                            // the group minima are dead once every lane holds its bound tau in a register
         unsigned short grp[G][32];     // [group][query]  bf16, rounded up (pass 1 -> bound)
-        KsSelect sel;                  // pass 2
+        KsSelect sel[S];               // pass 2: one scratch per slice (warp) of the query block
     };
 };
-static_assert(sizeof(KsSelect) <= sizeof(unsigned short) * 32 * 32, "KsSelect must fit under the group minima");
 
-template <int G, int NWARPS>
+// S > 1 ("slices"): S warps share one block of 32 queries -- in pass 1 each scans 1/S of the candidates (whole groups), in pass 2
+// each selects 32/S of the queries.  Used when the batch has too few queries to fill the chip with one warp per block (the
+// training shapes: 256..1024 queries per cloud); needs the single resident tile (n <= KS_TILE) and subgroups of <= 16.
+template <int G, int NWARPS, int S>
 __global__ void __launch_bounds__(NWARPS * 32) knn_select_kernel(const float* __restrict__ xyz, const float* __restrict__ new_xyz,
                                                                 int n, int m, int k, int log2ss, int gsz, int* __restrict__ idx,
                                                                 float* __restrict__ dist2) {
     constexpr int THREADS = NWARPS * 32;
+    constexpr int NQ = NWARPS / S;  // query blocks per CTA
     extern __shared__ __align__(16) unsigned char smem_raw[];
     float* tile = reinterpret_cast<float*>(smem_raw);  // [3][KS_TILE]
-    KsWarp<G>* wsm = reinterpret_cast<KsWarp<G>*>(tile + 3 * KS_TILE) + (threadIdx.x >> 5);
-
     const int bz = blockIdx.y, t = threadIdx.x, lane = t & 31, warp = t >> 5;
+    const int qblock = warp / S, slice = warp % S;
+    KsWarp<G, S>* wsm = reinterpret_cast<KsWarp<G, S>*>(tile + 3 * KS_TILE) + qblock;
+    KsSelect& sel = wsm->sel[slice];
+
     const int ss = 1 << log2ss;
     const int nsub = (n + ss - 1) >> log2ss;          // <= KS_NSUB
     const int ng = (nsub + gsz - 1) / gsz;            // <= G
     const float* pb = xyz + (size_t)bz * n * 3;
-    const int q0 = blockIdx.x * THREADS + warp * 32;  // first query of this warp
-    const int qmine = min(q0 + lane, m - 1);
+    const int q0 = (blockIdx.x * NQ + qblock) * 32;   // first query of this block
+    const int qmine = max(0, min(q0 + lane, m - 1));
     const float* qp = new_xyz + ((size_t)bz * m + qmine) * 3;
     const float qx = qp[0], qy = qp[1], qz = qp[2];
 
@@ -257,12 +262,22 @@ __global__ void __launch_bounds__(NWARPS * 32) knn_select_kernel(const float* __
     // Candidates are walked in blocks of 16 (4 quads, fully unrolled, each quad loaded one quad ahead); a block yields its
     // four quad minima, which are then emitted at the subgroup granularity (ss = 4, 8, 16, or a multiple of 16).
     {
+        // slice `slice` owns the candidate blocks [jb0, jb1) of the (single) tile: whole groups of subgroups
+        int jb0 = 0, jb1 = KS_TILE;
+        if (S > 1) {
+            const int unit = max(16, ss * gsz);
+            const int units = (((min(KS_TILE, n) + 15) & ~15) + unit - 1) / unit;
+            const int per = (units + S - 1) / S;
+            jb0 = slice * per * unit;
+            jb1 = jb0 + per * unit;
+        }
+        const int sg0 = jb0 >> log2ss;                     // first subgroup of the slice (a multiple of gsz)
         float gmn = kInf;
         int gleft = gsz;                                   // subgroups left in the current group
-        unsigned short* subrow = &wsm->sub[0][0];          // row of the current subgroup
-        unsigned short* grow = &wsm->grp[0][lane];
-        int col = lane;                                    // (lane + sg) & 31
-        int sgi = 0;                                       // subgroups emitted so far
+        unsigned short* subrow = &wsm->sub[min(sg0, KS_NSUB - 1)][0];           // row of the current subgroup
+        unsigned short* grow = &wsm->grp[min(sg0 / gsz, G - 1)][lane];
+        int col = (lane + sg0) & 31;                       // (lane + sg) & 31
+        int sgi = sg0;                                     // index of the next subgroup to emit
         auto emit = [&](float mn) {
             if (sgi < nsub) {                              // (the NaN padding of the last block can start an extra one)
                 subrow[col] = (unsigned short)(__float_as_uint(mn) >> 16);   // toward zero = down (mn >= 0)
@@ -285,10 +300,11 @@ __global__ void __launch_bounds__(NWARPS * 32) knn_select_kernel(const float* __
             ks_load_tile<THREADS>(tile, pb, j0, cnt, t);
             __syncthreads();
             const int cnt16 = (cnt + 15) & ~15;
-            float4 X = *reinterpret_cast<const float4*>(tile);
-            float4 Y = *reinterpret_cast<const float4*>(tile + KS_TILE);
-            float4 Z = *reinterpret_cast<const float4*>(tile + 2 * KS_TILE);
-            for (int jb = 0; jb < cnt16; jb += 16) {
+            const int jbeg = min(jb0, cnt16 - 16), jend = min(jb1, cnt16);   // (an empty slice reads a valid quad, then loops 0 times)
+            float4 X = *reinterpret_cast<const float4*>(tile + jbeg);
+            float4 Y = *reinterpret_cast<const float4*>(tile + KS_TILE + jbeg);
+            float4 Z = *reinterpret_cast<const float4*>(tile + 2 * KS_TILE + jbeg);
+            for (int jb = jb0; jb < jend; jb += 16) {
                 float mq[4];
 #pragma unroll
                 for (int q = 0; q < 4; ++q) {
@@ -324,7 +340,8 @@ __global__ void __launch_bounds__(NWARPS * 32) knn_select_kernel(const float* __
         if (gleft != gsz) *grow = (unsigned short)((__float_as_uint(gmn) + 0xffffu) >> 16);  // ragged last group
     }
 
-    // ---------------- bound: tau = k-th smallest group minimum (own column only)
+    if (S > 1) __syncthreads();  // the minima of all slices are in shared memory
+    // ---------------- bound: tau = k-th smallest group minimum (own column only; every slice computes all 32 bounds)
     float tau;
     {
         float v[G];
@@ -337,13 +354,14 @@ __global__ void __launch_bounds__(NWARPS * 32) knn_select_kernel(const float* __
 #pragma unroll
         for (int g = 0; g < G; ++g) tau = (g < k) ? fmaxf(tau, v[g]) : tau;
     }
-    __syncwarp();
+    if (S > 1) __syncthreads();  // every slice has read the group minima: their storage becomes the selection scratch
+    else __syncwarp();
 
     // ---------------- pass 2: warp-cooperative selection, one query at a time
     const unsigned lt = (1u << lane) - 1u;
     const int nq = min(32, m - q0);
     const bool resident = n <= KS_TILE;  // the single tile of pass 1 is still in shared memory
-    for (int qi = 0; qi < nq; ++qi) {
+    for (int qi = slice; qi < nq; qi += S) {
         // NaN and +inf never survive: the bound is clamped to the largest finite float
         const float tq = fminf(__shfl_sync(kFull, tau, qi), 3.402823466e+38f);
         const float ax = __shfl_sync(kFull, qx, qi), ay = __shfl_sync(kFull, qy, qi), az = __shfl_sync(kFull, qz, qi);
@@ -356,7 +374,7 @@ __global__ void __launch_bounds__(NWARPS * 32) knn_select_kernel(const float* __
         for (int i = 0; i < KS_NSUB / 32; ++i) {
             const bool p = (unsigned)sp[i * 32 * 32] <= tq16;
             const unsigned mask = __ballot_sync(kFull, p);
-            if (p) wsm->sel.plist[npass + __popc(mask & lt)] = (unsigned short)(lane + 32 * i);
+            if (p) sel.plist[npass + __popc(mask & lt)] = (unsigned short)(lane + 32 * i);
             npass += __popc(mask);
         }
         __syncwarp();
@@ -367,7 +385,7 @@ __global__ void __launch_bounds__(NWARPS * 32) knn_select_kernel(const float* __
         for (int p0 = 0; p0 < total; p0 += 128) {
             const int p = p0 + 4 * lane;
             const bool ok = p < total;
-            const int sg = wsm->sel.plist[ok ? (p >> log2ss) : 0];
+            const int sg = sel.plist[ok ? (p >> log2ss) : 0];
             const int j = (sg << log2ss) + (p & (ss - 1));  // multiple of 4; j..j+3 stay inside the subgroup
             const float tql = ok ? tq : -1.0f;              // lanes past the end of the list keep nothing
             float d[4];
@@ -394,7 +412,7 @@ __global__ void __launch_bounds__(NWARPS * 32) knn_select_kernel(const float* __
                 const bool keep = d[u] <= tql;  // false for NaN
                 const unsigned mk = __ballot_sync(kFull, keep);
                 const int pos = nsurv + __popc(mk & lt);
-                if (keep && pos < KS_SCAP) wsm->sel.key[pos] = ((unsigned long long)__float_as_uint(d[u]) << 32) | (unsigned)(j + u);
+                if (keep && pos < KS_SCAP) sel.key[pos] = ((unsigned long long)__float_as_uint(d[u]) << 32) | (unsigned)(j + u);
                 nsurv += __popc(mk);
             }
         }
@@ -406,15 +424,15 @@ __global__ void __launch_bounds__(NWARPS * 32) knn_select_kernel(const float* __
             for (int e0 = 0; e0 < nsurv; e0 += 32) {
                 const int e = e0 + lane;
                 const bool have = e < nsurv;
-                const unsigned long long ke = have ? wsm->sel.key[e] : ~0ull;
+                const unsigned long long ke = have ? sel.key[e] : ~0ull;
                 int rank = 0;
                 int f = 0;
                 for (; f + 2 <= nsurv; f += 2) {
-                    const ulonglong2 kf = *reinterpret_cast<const ulonglong2*>(wsm->sel.key + f);
+                    const ulonglong2 kf = *reinterpret_cast<const ulonglong2*>(sel.key + f);
                     rank += (kf.x < ke) ? 1 : 0;
                     rank += (kf.y < ke) ? 1 : 0;
                 }
-                if (f < nsurv) rank += (wsm->sel.key[f] < ke) ? 1 : 0;
+                if (f < nsurv) rank += (sel.key[f] < ke) ? 1 : 0;
                 if (have && rank < k) {
                     oi[rank] = (int)(unsigned)ke;
                     if (od) od[rank] = __uint_as_float((unsigned)(ke >> 32));
@@ -426,8 +444,8 @@ __global__ void __launch_bounds__(NWARPS * 32) knn_select_kernel(const float* __
             }
         } else if (lane == 0) {
             // survivor overflow: exact serial scan of every candidate for this query (the key array doubles as the list)
-            float* ldl = reinterpret_cast<float*>(wsm->sel.key);
-            int* lil = reinterpret_cast<int*>(wsm->sel.key) + KS_SCAP;
+            float* ldl = reinterpret_cast<float*>(sel.key);
+            int* lil = reinterpret_cast<int*>(sel.key) + KS_SCAP;
             for (int e = 0; e < k; ++e) {
                 ldl[e] = kInf;
                 lil[e] = 0;
@@ -450,13 +468,14 @@ __global__ void __launch_bounds__(NWARPS * 32) knn_select_kernel(const float* __
     }
 }
 
-template <int G, int NWARPS>
+template <int G, int NWARPS, int S = 1>
 static int launch_select(const float* xyz, const float* new_xyz, int b, int n, int m, int k, int log2ss, int gsz, int* idx,
                          float* dist2, cudaStream_t st) {
-    const size_t smem = (size_t)3 * KS_TILE * 4 + (size_t)NWARPS * sizeof(KsWarp<G>);
-    PDGN_CUDA(cudaFuncSetAttribute(knn_select_kernel<G, NWARPS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    dim3 grid((m + NWARPS * 32 - 1) / (NWARPS * 32), b);
-    knn_select_kernel<G, NWARPS><<<grid, NWARPS * 32, smem, st>>>(xyz, new_xyz, n, m, k, log2ss, gsz, idx, dist2);
+    constexpr int NQ = NWARPS / S;
+    const size_t smem = (size_t)3 * KS_TILE * 4 + (size_t)NQ * sizeof(KsWarp<G, S>);
+    PDGN_CUDA(cudaFuncSetAttribute(knn_select_kernel<G, NWARPS, S>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    dim3 grid((m + NQ * 32 - 1) / (NQ * 32), b);
+    knn_select_kernel<G, NWARPS, S><<<grid, NWARPS * 32, smem, st>>>(xyz, new_xyz, n, m, k, log2ss, gsz, idx, dist2);
     PDGN_CHECK_LAUNCH();
     return PDGN_OK;
 }
@@ -500,9 +519,17 @@ static int knn_dispatch(const float* xyz, const float* new_xyz, int b, int n, in
     const long long want = 132;  // ~0.9 x SMs: one full wave of the widest CTA beats two waves of narrower ones
     const int width = (long long)((m + 511) / 512) * b >= want ? 16 : (long long)((m + 255) / 256) * b >= want ? 8
                     : (long long)((m + 127) / 128) * b >= want ? 4 : 2;
+    // fewer than ~132 CTAs even at 8 / 4 / 2 query blocks per CTA: S = 2 / 4 / 4 slices per block instead of narrower CTAs
+    static const bool no_slices = getenv("PDGN_KNN_NOSLICES") != nullptr;  // tuning hook
 #define PDGN_KS_LAUNCH(G_)                                                                                        \
     do {                                                                                                          \
+        const bool sliced = !no_slices && n <= KS_TILE && log2ss <= 4;                                            \
         if (width == 16) return launch_select<G_, 16>(xyz, new_xyz, b, n, m, k, log2ss, gsz, idx, dist2, st);     \
+        if (sliced) {                                                                                             \
+            if (width == 8) return launch_select<G_, 16, 2>(xyz, new_xyz, b, n, m, k, log2ss, gsz, idx, dist2, st); \
+            if (width == 4) return launch_select<G_, 16, 4>(xyz, new_xyz, b, n, m, k, log2ss, gsz, idx, dist2, st); \
+            return launch_select<G_, 8, 4>(xyz, new_xyz, b, n, m, k, log2ss, gsz, idx, dist2, st);                \
+        }                                                                                                         \
         if (width == 8) return launch_select<G_, 8>(xyz, new_xyz, b, n, m, k, log2ss, gsz, idx, dist2, st);       \
         if (width == 4) return launch_select<G_, 4>(xyz, new_xyz, b, n, m, k, log2ss, gsz, idx, dist2, st);       \
         return launch_select<G_, 2>(xyz, new_xyz, b, n, m, k, log2ss, gsz, idx, dist2, st);                       \

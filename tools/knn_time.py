@@ -21,6 +21,11 @@ for (b, n, k) in [(35, 2048, 20), (35, 1024, 20), (35, 512, 20), (35, 256, 20), 
     ms = t(lambda: ops.knn_xyz(k, xyz))
     print("b%d n%d k%d %.4f ms |" % (b, n, k, ms), end=" ")
 print()
+for (b, n, m, k) in [(35, 2048, 256, 20), (35, 2048, 512, 20), (35, 2048, 1024, 20), (35, 512, 256, 20)]:
+    xyz = (torch.rand(b, n, 3, generator=g) * 2 - 1).to(dev)
+    q = (torch.rand(b, m, 3, generator=g) * 2 - 1).to(dev)
+    print("b%d n%d m%d k%d %.4f ms |" % (b, n, m, k, t(lambda: ops.knn_xyz(k, xyz, q))), end=" ")
+print()
 for (b, n, m) in [(35, 2048, 1024), (35, 1024, 512), (35, 512, 256)]:
     unk = (torch.rand(b, n, 3, generator=g) * 2 - 1).to(dev)
     kn = (torch.rand(b, m, 3, generator=g) * 2 - 1).to(dev)
