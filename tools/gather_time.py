@@ -22,3 +22,15 @@ for (b, c, n, k) in [(35, 256, 1024, 10), (35, 128, 512, 10), (35, 64, 256, 10)]
     ms2 = bench._time_ms(lambda: ops.edge_feat_bwd(gee, idx64, c), 10, flush)
     gb2 = (gee.numel() + 2 * b * c * n) * 4 / 1e9 + idx64.numel() * 8 / 1e9
     print("B%d C%d N%d k%d: group_bwd %.1f us (%.0f GB/s)   edge_feat_bwd %.1f us (%.0f GB/s)" % (b, c, n, k, ms * 1e3, gb / ms * 1e3, ms2 * 1e3, gb2 / ms2 * 1e3), flush=True)
+
+from pdgn_b200._lib import lib
+L = lib()
+st = torch.cuda.current_stream().cuda_stream
+for (b, c, m, n) in [(35, 256, 1024, 2048), (35, 128, 512, 1024), (35, 64, 256, 512)]:
+    feat = torch.randn(b, c, m, device=dev)
+    idx3 = torch.from_numpy(rng.integers(0, m, (b, n, 3)).astype(np.int32)).to(dev)
+    w3 = torch.rand(b, n, 3, device=dev)
+    out = torch.empty(b, c, n, device=dev)
+    ms = bench._time_ms(lambda: L.pdgn_interp_fwd(feat.data_ptr(), idx3.data_ptr(), w3.data_ptr(), b, c, m, n, out.data_ptr(), st), 10, flush)
+    gb = (feat.numel() + out.numel() + 2 * idx3.numel()) * 4 / 1e9
+    print("interp fwd B%d C%d m%d n%d: %.1f us (%.0f GB/s) [PDGN_IS_ROW_KB=%s]" % (b, c, m, n, ms * 1e3, gb / ms * 1e3, os.environ.get("PDGN_IS_ROW_KB", "default")), flush=True)
