@@ -51,6 +51,62 @@ def max_tile(world, n_rows, n_cols):
     return -(-n_rows // pr), -(-n_cols // pc)
 
 
+def sym_plan(world, n, blocks_per_rank=4):
+    """Same-set matrix (rr / ss of compute_all_metrics): CD(a, b) == CD(b, a), so only the block pairs (i <= j) of a
+    T x T block grid are computed, T = blocks_per_rank * world.  Returns (bounds, owner) with bounds[i] = (lo, hi) of block i
+    and owner = list over ranks of their [(i, j), ...] tiles, assigned largest-first to the least loaded rank (a diagonal
+    tile costs half: the kernel walks its upper triangle only).  Deterministic: every rank derives the same plan."""
+    t = max(1, min(n, blocks_per_rank * world))
+    bounds = [split(n, t, i) for i in range(t)]
+    size = [hi - lo for lo, hi in bounds]
+    tiles = [(i, j) for i in range(t) for j in range(i, t)]
+    cost = {(i, j): size[i] * size[j] * (0.5 if i == j else 1.0) for i, j in tiles}
+    tiles.sort(key=lambda ij: (-cost[ij], ij))
+    load = [0.0] * world
+    owner = [[] for _ in range(world)]
+    for ij in tiles:
+        r = min(range(world), key=lambda q: (load[q], q))
+        owner[r].append(ij)
+        load[r] += cost[ij]
+    return bounds, owner
+
+
+def pairwise_cd_symmetric(pcs, group=None, compute_tile=None):
+    """Full [N, N] Chamfer matrix of a cloud set against itself on every rank, computing every unordered pair once."""
+    world = dist_.get_world_size(group)
+    rank = dist_.get_rank(group)
+    n = pcs.shape[0]
+    if compute_tile is None:
+        compute_tile = ops.cd_allpairs
+    bounds, owner = sym_plan(world, n)
+    area = lambda ij: (bounds[ij[0]][1] - bounds[ij[0]][0]) * (bounds[ij[1]][1] - bounds[ij[1]][0])
+    longest = max(sum(area(ij) for ij in tiles) for tiles in owner)
+    mine = pcs.new_zeros((max(longest, 1),))
+    at = 0
+    for ij in owner[rank]:
+        rows, cols = bounds[ij[0]], bounds[ij[1]]
+        if rows[1] > rows[0] and cols[1] > cols[0]:
+            mine[at: at + area(ij)] = compute_tile(pcs, pcs, rows, cols).reshape(-1)
+        at += area(ij)
+    gathered = [torch.empty_like(mine) for _ in range(world)]
+    dist_.all_gather(gathered, mine, group=group)
+    full = mine.new_empty((n, n))
+    for r in range(world):
+        at = 0
+        for ij in owner[r]:
+            (r0, r1), (c0, c1) = bounds[ij[0]], bounds[ij[1]]
+            tile = gathered[r][at: at + area(ij)].view(r1 - r0, c1 - c0)
+            full[r0:r1, c0:c1] = tile
+            if ij[0] != ij[1]:
+                full[c0:c1, r0:r1] = tile.t()
+            at += area(ij)
+    return full
+
+
+def _same_set(a, b):
+    return a.shape == b.shape and a.data_ptr() == b.data_ptr() and a.stride() == b.stride()
+
+
 def pairwise_emd(sample_pcs, ref_pcs, group=None):
     """Full [N_sample, N_ref] approximate-EMD matrix on every rank (same tiling and collective as pairwise_cd)."""
     return pairwise_cd(sample_pcs, ref_pcs, group=group, compute_tile=ops.emd_allpairs)
@@ -62,9 +118,12 @@ def pairwise_cd(sample_pcs, ref_pcs, group=None, compute_tile=None):
     world = dist_.get_world_size(group)
     rank = dist_.get_rank(group)
     n_rows, n_cols = sample_pcs.shape[0], ref_pcs.shape[0]
-    rows, cols = tile_of(rank, world, n_rows, n_cols)
     if compute_tile is None:
+        # rr / ss matrices: every unordered pair once (CD is symmetric); below ~128 clouds the extra launches cost more
+        if _same_set(sample_pcs, ref_pcs) and n_rows >= 128:
+            return pairwise_cd_symmetric(sample_pcs, group=group)
         compute_tile = ops.cd_allpairs
+    rows, cols = tile_of(rank, world, n_rows, n_cols)
     mr, mc = max_tile(world, n_rows, n_cols)
     mine = sample_pcs.new_zeros((mr, mc))
     if rows[1] > rows[0] and cols[1] > cols[0]:

@@ -72,3 +72,66 @@ def test_all_gather_path_world2_gloo(na, nb):
         assert p.exitcode == 0
     assert sorted(r[0] for r in res) == [0, 1]
     assert all(ok and shape == (na, nb) for _, ok, shape in res)
+
+
+@pytest.mark.parametrize("world", [1, 2, 3, 4, 8])
+@pytest.mark.parametrize("n", [1000, 7, 1, 64, 33])
+def test_symmetric_plan_covers_every_unordered_block_pair_once_and_is_balanced(world, n):
+    from pdgn_b200 import dist as pd
+    bounds, owner = pd.sym_plan(world, n)
+    t = len(bounds)
+    assert bounds[0][0] == 0 and bounds[-1][1] == n and all(bounds[i][1] == bounds[i + 1][0] for i in range(t - 1))
+    seen = sorted(ij for tiles in owner for ij in tiles)
+    assert seen == [(i, j) for i in range(t) for j in range(i, t)]
+    cover = np.zeros((n, n), dtype=np.int32)
+    for tiles in owner:
+        for i, j in tiles:
+            (r0, r1), (c0, c1) = bounds[i], bounds[j]
+            cover[r0:r1, c0:c1] += 1
+            if i != j:
+                cover[c0:c1, r0:r1] += 1
+    assert np.all(cover == 1)
+    if n >= 64 * world:  # enough blocks: no rank carries more than ~15 % over the mean
+        size = [hi - lo for lo, hi in bounds]
+        load = [sum(size[i] * size[j] * (0.5 if i == j else 1.0) for i, j in tiles) for tiles in owner]
+        assert max(load) <= 1.15 * (sum(load) / world)
+
+
+def _worker_sym(rank, world, port, n, npts, q):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    sys.path.insert(0, ROOT)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        from oracle import cpu as ocpu
+        from pdgn_b200 import dist as pd
+        rng = np.random.default_rng(3)
+        A = torch.from_numpy(rng.uniform(-1, 1, (n, npts, 3)).astype(np.float32))
+        calls = []
+
+        def cpu_tile(a, b, rows, cols):
+            calls.append((rows, cols))
+            return torch.from_numpy(ocpu.cd_allpairs(a[rows[0]:rows[1]].numpy(), b[cols[0]:cols[1]].numpy()))
+
+        full = pd.pairwise_cd_symmetric(A, compute_tile=cpu_tile)
+        ref = torch.from_numpy(ocpu.cd_allpairs(A.numpy(), A.numpy()))
+        pairs = sum((r[1] - r[0]) * (c[1] - c[0]) for r, c in calls)
+        q.put((rank, bool(torch.equal(full, ref)), tuple(full.shape), pairs))
+    finally:
+        dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("n", [9, 16, 2])
+def test_symmetric_all_gather_path_world2_gloo(n):
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = 29500 + (os.getpid() + n * 31 + 7) % 400
+    procs = [ctx.Process(target=_worker_sym, args=(r, 2, port, n, 48, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    res = [q.get(timeout=120) for _ in procs]
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    assert all(ok and shape == (n, n) for _, ok, shape, _ in res)
+    # together the ranks evaluated the upper triangle (diagonal blocks in full): fewer pairs than the n*n of plain tiling
+    assert sum(r[3] for r in res) < n * n or n <= 2
