@@ -491,6 +491,40 @@ def test_streams_and_errors(dev):
         ops.knn_feat(torch.zeros(1, 4, 8, device=dev), 10)
 
 
+def test_workspace_and_size_errors_are_return_codes(dev):
+    """Workspace too small / misaligned and sizes outside the kernels' range come back as PDGN_ERR_* (raised as PdgnError),
+    never as a crash or a silent wrong answer."""
+    from pdgn_b200 import PdgnError, local_pair, ops
+    from pdgn_b200._lib import lib
+    L = lib()
+    st = torch.cuda.current_stream().cuda_stream
+    a, b = torch.rand(2, 64, 3, device=dev), torch.rand(3, 64, 3, device=dev)
+    out = torch.empty(2, 3, device=dev)
+    need = L.pdgn_emd_allpairs_workspace(2, 3, 64, 64)
+    ws = torch.empty(need, dtype=torch.uint8, device=dev)
+    args = (a.data_ptr(), b.data_ptr(), 2, 3, 64, 64, 0, 2, 0, 3, out.data_ptr(), 3)
+    assert L.pdgn_emd_allpairs(*args, ws.data_ptr(), need, st) == 0
+    assert L.pdgn_emd_allpairs(*args, ws.data_ptr(), 64, st) == -3            # PDGN_ERR_WORKSPACE
+    assert L.pdgn_emd_allpairs(*args, ws.data_ptr() + 4, need, st) == -3       # misaligned
+    assert L.pdgn_emd_allpairs(*args, None, need, st) == -3
+    with pytest.raises(PdgnError):
+        ops.emd_allpairs(torch.rand(1, 2049, 3, device=dev), torch.rand(1, 64, 3, device=dev))  # n > 2048: unsupported
+    need_cd = L.pdgn_cd_allpairs_workspace(2, 3, 64)
+    ws_cd = torch.empty(need_cd, dtype=torch.uint8, device=dev)
+    assert L.pdgn_cd_allpairs(a.data_ptr(), b.data_ptr(), 2, 3, 64, 0, 2, 0, 3, out.data_ptr(), 3, ws_cd.data_ptr(), 16, st) == -3
+    assert L.pdgn_cd_allpairs(a.data_ptr(), b.data_ptr(), 2, 3, 64, 0, 2, 0, 4, out.data_ptr(), 3, ws_cd.data_ptr(), need_cd, st) == -1
+    p1, p2 = torch.rand(2, 3, 40, device=dev), torch.rand(2, 3, 90, device=dev)
+    with pytest.raises(PdgnError):
+        local_pair._LocalPairCall.apply(p1, p2, 65)                              # k > 64: unsupported by the fused statistics
+    need_lp = L.pdgn_local_pair_workspace(2, 40, 90, 8)
+    ws_lp = torch.empty(need_lp, dtype=torch.uint8, device=dev)
+    o2 = torch.empty(2, device=dev)
+    assert L.pdgn_local_pair_fwd(p1.data_ptr(), p2.data_ptr(), 2, 40, 90, 8, o2.data_ptr(), ws_lp.data_ptr(), need_lp // 2, st) == -3
+    assert L.pdgn_local_pair_fwd(p1.data_ptr(), p2.data_ptr(), 2, 40, 90, 8, o2.data_ptr(), ws_lp.data_ptr(), need_lp, st) == 0
+    torch.cuda.synchronize()
+    assert torch.isfinite(o2).all() and torch.isfinite(out).all()
+
+
 # ------------------------------------------------------------------------------------------------ edge cases
 def test_empty_and_degenerate_inputs(dev):
     """Zero-sized batches / query sets / neighbour lists: no launch, correctly shaped empty outputs, no crash."""
