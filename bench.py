@@ -291,7 +291,9 @@ def main():
     obs_mhz = (clocks or {}).get("sm_mhz") or sm_max_mhz
     roofline = {
         "bound": "fp32", "kernel": "cd_allpairs_kernel", "achieved": achieved_tflops, "peak": peak_tflops, "unit": "TFLOP/s",
-        "frac": achieved_tflops / peak_tflops, "traffic": traffic_from_profile(nc, world),
+        "frac": achieved_tflops / peak_tflops,
+        # dram__bytes_read.sum + dram__bytes_write.sum of one launch (bytes), or null outside the captured configuration
+        "traffic": (traffic_from_profile(nc, world) or {}).get("bytes"), "traffic_detail": traffic_from_profile(nc, world),
         "kernel_ms": kernel_ms, "cloud_pairs_per_launch": tile_pairs,
         "definition": "achieved = cloud pairs x 2048^2 point pairs x 6 FMA-pipe instr x 2 FLOP-slots / kernel time (issue-rate "
                       "fraction == FMA-pipe utilisation, SURVEY.md 8d); peak = SMs x 128 lanes x 2 x sm_max_mhz (MEASURED_PEAKS.json)",
