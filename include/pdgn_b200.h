@@ -125,6 +125,13 @@ size_t pdgn_emd_allpairs_workspace(int nrows, int ncols, int n, int m);
 int pdgn_emd_allpairs(const float *A, const float *B, int na, int nb, int n, int m, int row0, int row1, int col0,
                       int col1, float *out, long long ld_out, void *workspace, size_t workspace_bytes, void *stream);
 
+/* Paired form of the same kernel: out[i] = match_cost(A_i, B_i) / n for i in [0,b) -- what MatchCostFunction.forward
+ * (evaluation/pytorch_structural_losses/match_cost.py:10-24) returns for a batch, divided by n as emd_approx does
+ * (evaluation_metrics.py:26-31); used by EMD_CD (:48-82).  One CTA per pair, all pairs in one launch. */
+size_t pdgn_emd_paired_workspace(int b, int n, int m);
+int pdgn_emd_paired(const float *A, const float *B, int b, int n, int m, float *out, void *workspace,
+                    size_t workspace_bytes, void *stream);
+
 /* ---- fused neighbourhood statistics (next row: the loss-side of get_local_pair) -------------------------------
  * Replaces grouping + transpose/view + compute_mean_covariance (lib/pointops/functions/pointops.py:699-703,
  * models/PDGNet_v2.py:127-134,142-147) for given kNN indices: xyz [b,n,3], idx int32 [b,m,k] ->

@@ -13,6 +13,8 @@ void nndistancegrad(int b, int n, const float *xyz1, int m, const float *xyz2, c
 
 void approxmatch(int b, int n, int m, const float *xyz1, const float *xyz2, float *match, float *temp, cudaStream_t stream);
 void matchcost(int b, int n, int m, const float *xyz1, const float *xyz2, float *match, float *out, cudaStream_t stream);
+void matchcostgrad(int b, int n, int m, const float *xyz1, const float *xyz2, const float *match, float *grad1, float *grad2,
+                   cudaStream_t stream);
 
 extern "C" {
 // ApproxMatch + MatchCost as MatchCostFunction.forward chains them (match_cost.py:21-23).
@@ -24,6 +26,19 @@ int ref_match_cost(int b, int n, int m, const float *xyz1, const float *xyz2, fl
     } catch (...) {
         return -1;
     }
+    return (int)cudaGetLastError();
+}
+// The three StructuralLossesBackend entry points one by one (pybind/bind.cpp:10-16), for oracle/ref_tree.py.
+int ref_approxmatch(int b, int n, int m, const float *xyz1, const float *xyz2, float *match, float *temp, void *stream) {
+    try { approxmatch(b, n, m, xyz1, xyz2, match, temp, (cudaStream_t)stream); } catch (...) { return -1; }
+    return (int)cudaGetLastError();
+}
+int ref_matchcost(int b, int n, int m, const float *xyz1, const float *xyz2, float *match, float *out, void *stream) {
+    try { matchcost(b, n, m, xyz1, xyz2, match, out, (cudaStream_t)stream); } catch (...) { return -1; }
+    return (int)cudaGetLastError();
+}
+int ref_matchcostgrad(int b, int n, int m, const float *xyz1, const float *xyz2, const float *match, float *g1, float *g2, void *stream) {
+    try { matchcostgrad(b, n, m, xyz1, xyz2, match, g1, g2, (cudaStream_t)stream); } catch (...) { return -1; }
     return (int)cudaGetLastError();
 }
 int ref_nndistance(int b, int n, const float *xyz, int m, const float *xyz2, float *d1, int *i1, float *d2, int *i2,

@@ -36,6 +36,8 @@ SIGNATURES = {
     "pdgn_cd_allpairs_host": (_I, [_P, _P, _I, _I, _I, _I, _I, _I, _I, _P, _LL, _P]),
     "pdgn_emd_allpairs_workspace": (_SZ, [_I, _I, _I, _I]),
     "pdgn_emd_allpairs": (_I, [_P, _P, _I, _I, _I, _I, _I, _I, _I, _I, _P, _LL, _P, _SZ, _P]),
+    "pdgn_emd_paired_workspace": (_SZ, [_I, _I, _I]),
+    "pdgn_emd_paired": (_I, [_P, _P, _I, _I, _I, _P, _P, _SZ, _P]),
     "pdgn_local_stats_fwd": (_I, [_P, _P, _I, _I, _I, _I, _P, _P, _P]),
     "pdgn_local_stats_bwd": (_I, [_P, _P, _P, _P, _P, _I, _I, _I, _I, _P, _P]),
     "pdgn_local_pair_workspace": (_SZ, [_I, _I, _I, _I]),

@@ -190,7 +190,7 @@ __device__ __forceinline__ void emd_transport_pass(const float4* __restrict__ Rr
 
 __global__ void __launch_bounds__(EM_T, 2)
 emd_allpairs_kernel(const float* __restrict__ A, const float* __restrict__ B, int ncols, int n, int m, int rstrip,
-                    float* __restrict__ out, long long ld_out) {
+                    float* __restrict__ out, long long ld_out, int paired) {
     extern __shared__ __align__(16) float4 em_sm[];
     float4* L = em_sm;                 // [EM_MAX] left cloud:  x, y, z, ratioL
     float4* Rr = em_sm + EM_MAX;       // [EM_MAX] right cloud: x, y, z, ratioR
@@ -201,7 +201,8 @@ emd_allpairs_kernel(const float* __restrict__ A, const float* __restrict__ B, in
     __shared__ float red[EM_T / 32];
     const int t = threadIdx.x, lane = t & 31, warp = t >> 5;
     const int s = blockIdx.y;
-    const int r_begin = blockIdx.x * rstrip, r_end = min(ncols, r_begin + rstrip);
+    // paired mode (match_cost.py:6-44 on a batch): row s meets column s only, out[s] (ld_out == 0)
+    const int r_begin = paired ? s : blockIdx.x * rstrip, r_end = paired ? s + 1 : min(ncols, r_begin + rstrip);
     const float multiL = n >= m ? 1.f : (float)(m / n), multiR = n >= m ? (float)(n / m) : 1.f;
     const int nchL = (n + EM_CH - 1) / EM_CH, nchR = (m + EM_CH - 1) / EM_CH;
     const int own0 = warp * EM_WPTS + lane;   // this thread owns points own0 + 32*i of each cloud: chunks 4*warp .. 4*warp+3
@@ -377,7 +378,34 @@ extern "C" int pdgn_emd_allpairs(const float* A, const float* B, int na, int nb,
     if (strips < 1) strips = 1;
     const int rstrip = (ncols + strips - 1) / strips;
     strips = (ncols + rstrip - 1) / rstrip;
-    emd_allpairs_kernel<<<dim3(strips, nrows), EM_T, smem, st>>>(SA, SB, ncols, n, m, rstrip, out, ld_out);
+    emd_allpairs_kernel<<<dim3(strips, nrows), EM_T, smem, st>>>(SA, SB, ncols, n, m, rstrip, out, ld_out, 0);
     PDGN_CHECK_LAUNCH();
+    return PDGN_OK;
+}
+
+extern "C" size_t pdgn_emd_paired_workspace(int b, int n, int m) { return pdgn_emd_allpairs_workspace(b, b, n, m); }
+
+extern "C" int pdgn_emd_paired(const float* A, const float* B, int b, int n, int m, float* out, void* workspace,
+                               size_t workspace_bytes, void* stream) {
+    if (b < 0 || n <= 0 || m <= 0) return PDGN_ERR_BAD_ARG;
+    if (n > EM_MAX || m > EM_MAX) return PDGN_ERR_UNSUPPORTED;
+    if (b == 0) return PDGN_OK;
+    if (!A || !B || !out) return PDGN_ERR_BAD_ARG;
+    const size_t need = ((size_t)b * n + (size_t)b * m) * 3 * sizeof(float);
+    if (!workspace || workspace_bytes < need || (reinterpret_cast<uintptr_t>(workspace) & 15)) return PDGN_ERR_WORKSPACE;
+    cudaStream_t st = (cudaStream_t)stream;
+    float* SA = reinterpret_cast<float*>(workspace);
+    float* SB = SA + (size_t)b * n * 3;
+    const size_t smem = (size_t)(2 * EM_MAX + 4 * EM_NCH + 4 * (EM_T / 32)) * sizeof(float4) + (size_t)EM_MAX * sizeof(float);
+    PDGN_CUDA(cudaFuncSetAttribute(emd_allpairs_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    for (int at = 0; at < b; at += 65535) {  // gridDim.y limit
+        const int cnt = b - at < 65535 ? b - at : 65535;
+        emd_sort_kernel<<<cnt, EM_SORT_T, 0, st>>>(A, at, n, SA + (size_t)at * n * 3);
+        PDGN_CHECK_LAUNCH();
+        emd_sort_kernel<<<cnt, EM_SORT_T, 0, st>>>(B, at, m, SB + (size_t)at * m * 3);
+        PDGN_CHECK_LAUNCH();
+        emd_allpairs_kernel<<<dim3(1, cnt), EM_T, smem, st>>>(SA + (size_t)at * n * 3, SB + (size_t)at * m * 3, cnt, n, m, 1, out + at, 0, 1);
+        PDGN_CHECK_LAUNCH();
+    }
     return PDGN_OK;
 }

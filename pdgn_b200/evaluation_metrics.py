@@ -10,7 +10,8 @@ pointed here (pdgn_b200.dropin).  What changes is where the work happens:
   * emd_approx / match_cost (:26-31, match_cost.py) and the EMD half of _pairwise_EMD_CD_: the all-pairs approximate-EMD
     kernel (csrc/emd.cu), forward only -- the reference uses EMD only in evaluation.
 Set PDGN_B200_SKIP_EMD=1 to skip the EMD matrices (they cost ~35x the CD ones): all_emd is then None and the *-EMD keys
-are omitted.
+are omitted.  Limit: the EMD kernel handles clouds of at most EMD_MAX_POINTS = 2048 points (every PDGN configuration); larger
+clouds raise ValueError unless EMD is skipped.  The CD kernels take up to 16384 points per cloud.
 """
 import os
 import warnings
@@ -20,6 +21,9 @@ import torch
 
 from . import ops
 from .chamfer_loss import chamfer_min
+
+
+EMD_MAX_POINTS = 2048
 
 
 def distChamferCUDA(x, y):
@@ -37,11 +41,14 @@ def match_cost(seta, setb):
     """match_cost.py:6-44, forward only: per-pair approximate-EMD matching cost [B] of seta [B,n,3] vs setb [B,m,3]."""
     seta = seta.detach().contiguous().float()
     setb = setb.detach().contiguous().float()
-    n = seta.size(1)
-    out = torch.empty((seta.size(0),), dtype=torch.float32, device=seta.device)
-    for i in range(seta.size(0)):  # paired form = diagonal of the all-pairs problem, one 1x1 tile per pair
-        out[i:i + 1] = ops.emd_allpairs(seta, setb, rows=(i, i + 1), cols=(i, i + 1)).view(1) * float(n)
-    return out
+    _check_emd_size(seta.size(1), setb.size(1))
+    return ops.emd_paired(seta, setb) * float(seta.size(1))      # one launch, one CTA per pair
+
+
+def _check_emd_size(n, m):
+    if n > EMD_MAX_POINTS or m > EMD_MAX_POINTS:
+        raise ValueError("pdgn_b200: the approximate-EMD kernel keeps both clouds on chip and handles at most %d points per "
+                         "cloud (got %d and %d); set PDGN_B200_SKIP_EMD=1 to compute the CD metrics only" % (EMD_MAX_POINTS, n, m))
 
 
 def emd_approx(sample, ref):
@@ -77,6 +84,8 @@ def _pairwise_EMD_CD_(sample_pcs, ref_pcs, batch_size=None, accelerated_cd=True)
     sample_pcs = sample_pcs.contiguous().float()
     ref_pcs = ref_pcs.contiguous().float()
     skip = _skip_emd()
+    if not skip:
+        _check_emd_size(sample_pcs.size(1), ref_pcs.size(1))
     if dist.is_distributed():
         return dist.pairwise_cd(sample_pcs, ref_pcs), (None if skip else dist.pairwise_emd(sample_pcs, ref_pcs))
     return ops.cd_allpairs(sample_pcs, ref_pcs), (None if skip else ops.emd_allpairs(sample_pcs, ref_pcs))
@@ -146,10 +155,17 @@ def compute_all_metrics(sample_pcs, ref_pcs, batch_size=None, accelerated_cd=Fal
 #######################################################
 # JSD (evaluation_metrics.py:206-321) -- next row 8f-4
 #######################################################
+def _grid_axis(resolution):
+    """The per-axis cell centres exactly as the reference stores them: i * spacing - 0.5 in double, rounded to float32
+    (evaluation_metrics.py:211-218)."""
+    spacing = 1.0 / float(resolution - 1)
+    return np.array([i * spacing - 0.5 for i in range(resolution)], dtype=np.float64).astype(np.float32)
+
+
 def unit_cube_grid_point_cloud(resolution, clip_sphere=False):
     """evaluation_metrics.py:206-224: centres of a resolution^3 grid in the unit cube (numpy, as the reference returns)."""
     spacing = 1.0 / float(resolution - 1)
-    ax = (np.arange(resolution, dtype=np.float32) * np.float32(spacing) - np.float32(0.5)).astype(np.float32)
+    ax = _grid_axis(resolution)
     grid = np.stack(np.meshgrid(ax, ax, ax, indexing="ij"), axis=-1).astype(np.float32)
     if clip_sphere:
         grid = grid.reshape(-1, 3)
@@ -157,14 +173,31 @@ def unit_cube_grid_point_cloud(resolution, clip_sphere=False):
     return grid, spacing
 
 
+_JSD_RERANK = 8
+
+
 def _nearest_grid_index(points, resolution, in_sphere):
-    """Index (into the possibly sphere-clipped grid list) of the nearest grid centre for every point [P,3] on the GPU.
-    The nearest centre of the FULL regular grid is a rounding; it is also the nearest ALLOWED centre whenever it lies inside
-    the sphere (true for all but a handful of boundary points), and those few go through the exact 1-NN kernel."""
+    """Index (into the possibly sphere-clipped grid list) of the nearest grid centre for every point [P,3], reproducing the
+    reference's sklearn NearestNeighbors(n_neighbors=1) answer (float64 Euclidean distances to the float32 cell centres,
+    evaluation_metrics.py:262-266) EXACTLY rather than to FP32 rounding:
+      * the squared distance to a regular grid is separable, so the nearest centre of the FULL grid is the per-axis nearest;
+        it is found in float64 among the rounded cell and its two neighbours (float32 differences are exact in float64);
+      * when that centre lies inside the sphere it is also the nearest ALLOWED one; the few boundary points for which it
+        does not go through the exact FP32 kNN kernel for the %d best allowed centres, re-ranked in float64.""" % _JSD_RERANK
     dev = points.device
     spacing = 1.0 / float(resolution - 1)
-    cell = torch.clamp(torch.round((points + 0.5) / spacing), 0, resolution - 1).long()
-    flat = (cell[:, 0] * resolution + cell[:, 1]) * resolution + cell[:, 2]
+    axis = torch.from_numpy(_grid_axis(resolution).astype(np.float64)).to(dev)
+    p64 = points.double()
+    cell = torch.clamp(torch.round((p64 + 0.5) / spacing), 0, resolution - 1).long()
+    best = cell
+    best_d = (p64 - axis[cell]).abs()
+    for off in (-1, 1):
+        cand = torch.clamp(cell + off, 0, resolution - 1)
+        d = (p64 - axis[cand]).abs()
+        take = (d < best_d) | ((d == best_d) & (cand < best))
+        best = torch.where(take, cand, best)
+        best_d = torch.where(take, d, best_d)
+    flat = (best[:, 0] * resolution + best[:, 1]) * resolution + best[:, 2]
     if not in_sphere:
         return flat, resolution ** 3
     grid_np, _ = unit_cube_grid_point_cloud(resolution, True)
@@ -175,9 +208,14 @@ def _nearest_grid_index(points, resolution, in_sphere):
     out = lut[flat]
     miss = out < 0
     if bool(miss.any()):
-        grid = torch.from_numpy(grid_np).to(dev).unsqueeze(0).contiguous()
-        q = points[miss].unsqueeze(0).contiguous()
-        out[miss] = ops.knn_xyz(1, grid, q).view(-1).long()
+        grid = torch.from_numpy(grid_np).to(dev)
+        q = points[miss].contiguous()
+        k = min(_JSD_RERANK, grid.shape[0])
+        cand = ops.knn_xyz(k, grid.unsqueeze(0).contiguous(), q.unsqueeze(0).contiguous()).view(-1, k).long()
+        d2 = (q.double().unsqueeze(1) - grid.double()[cand]).pow(2).sum(dim=2)            # [Q, k] float64
+        dmin = d2.min(dim=1, keepdim=True).values
+        pick = torch.where(d2 == dmin, cand, torch.full_like(cand, grid.shape[0])).min(dim=1).values   # lowest index among equals
+        out[miss] = pick
     return out, int(keep.sum())
 
 

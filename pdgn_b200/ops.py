@@ -165,6 +165,22 @@ def emd_allpairs(A, B, rows=None, cols=None, out=None):
     return out
 
 
+def emd_paired(A, B):
+    """Approximate EMD of A[i] vs B[i]: A [b,n,3], B [b,m,3] -> [b] of match_cost / n (no gradient), one launch."""
+    _req(A, "A"); _req(B, "B")
+    b, n, _ = A.shape
+    if B.shape[0] != b:
+        raise ValueError("paired EMD needs equal batch sizes")
+    m = B.shape[1]
+    out = torch.empty((b,), dtype=torch.float32, device=A.device)
+    L = lib()
+    ws_bytes = L.pdgn_emd_paired_workspace(b, n, m)
+    ws = torch.empty((ws_bytes,), dtype=torch.uint8, device=A.device)
+    with torch.cuda.device(A.device):
+        check(L.pdgn_emd_paired(A.data_ptr(), B.data_ptr(), b, n, m, out.data_ptr(), ws.data_ptr(), ws_bytes, _stream(A)), "pdgn_emd_paired")
+    return out
+
+
 def cd_allpairs_host(A, B, rows=None, cols=None):
     """Same, for CPU (ideally pinned) tensors: H2D + kernel + D2H inside the C call; returns a CPU tensor."""
     if A.is_cuda or B.is_cuda:

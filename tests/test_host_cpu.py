@@ -47,3 +47,29 @@ def test_jsd_arithmetic_matches_reference(golden):
     assert full.shape == (5, 5, 5, 3) and full[4, 0, 2].tolist() == [0.5, -0.5, 0.0]
     with pytest.raises(ValueError):
         em.jensen_shannon_divergence(np.array([1.0, -1.0]), np.array([1.0, 1.0]))
+
+
+def test_jsd_nearest_cell_is_exactly_sklearns(golden, monkeypatch):
+    """The cell assignment (analytic per-axis nearest in float64 + float64 re-rank of the sphere-boundary points) against
+    sklearn's NearestNeighbors on the reference's float32 grid -- what evaluation_metrics.py:262-266 runs -- with the kNN
+    kernel replaced by the CPU oracle (host logic only; the GPU test runs the real kernel against the golden counters)."""
+    from sklearn.neighbors import NearestNeighbors
+    from oracle import cpu as ocpu
+    from pdgn_b200 import evaluation_metrics as em
+
+    def oracle_knn(k, xyz, new_xyz):
+        return torch.from_numpy(ocpu.knn_xyz(xyz.numpy(), new_xyz.numpy(), k)[0])
+
+    monkeypatch.setattr(em.ops, "knn_xyz", oracle_knn)
+    g = golden("evaluation_metrics")
+    grid, _ = em.unit_cube_grid_point_cloud(28, True)
+    nn = NearestNeighbors(n_neighbors=1).fit(grid)
+    rng = np.random.default_rng(11)
+    on_sphere = rng.standard_normal((20000, 3))
+    on_sphere = (0.5 * on_sphere / np.linalg.norm(on_sphere, axis=1, keepdims=True)).astype(np.float32)
+    for pts in (g["jsd_smp"].reshape(-1, 3), rng.uniform(-0.5, 0.5, (20000, 3)).astype(np.float32), on_sphere):
+        idx, n_cells = em._nearest_grid_index(T(pts), 28, True)
+        assert n_cells == len(grid)
+        assert np.array_equal(idx.numpy(), nn.kneighbors(pts)[1][:, 0])
+    idx, _ = em._nearest_grid_index(T(g["jsd_ref"].reshape(-1, 3)), 28, True)
+    assert np.array_equal(np.bincount(idx.numpy(), minlength=len(grid)).astype(np.float64), g["jsd_counters_ref"])
