@@ -15,6 +15,13 @@ One JSON line on rank 0:
   roofline       FP32-SIMT roofline of the dominant kernel (cd_allpairs_kernel): 6 FMA-pipe instructions per point pair
   cpu_baseline   the reference's CPU formulation (oracle.torch_ref.pairwise_cd = distChamfer loop) on a bounded sample
   knnquery       secondary metric of BASELINE.json (Mqueries/s, k=20, B=35 x 2048) measured in the same run
+  reference_gpu  "reference on B200" (SURVEY.md 8d): the reference's torch Gram-form distChamfer loop and its NNDistance
+                 kernel (recompiled for sm_100a) on THIS GPU, on a bounded sample of the same workload; plus the reference's
+                 real _pairwise_EMD_CD_ (CD + EMD) against ours with EMD on
+  cfg3           BASELINE configs[2]: loss side of one G step (6 x get_local_pair, B=35) fwd+bwd, the four feature-space kNN
+                 stages fwd+bwd, and one generator step of the reference's own PointGenerator through the drop-in
+  cfg5           BASELINE configs[4]: knnquery k=32 on [8,16384,3] / [35,16384,3]; with --gpus 8 also one 4096x4096 CD matrix
+  eval_emd       compute_all_metrics (3 CD + 3 EMD matrices, 1000 x 1000 clouds) from host tensors, end to end
 `--impl reference` times only the CPU formulation (rank 0; other ranks exit 0).
 """
 import argparse
@@ -103,18 +110,48 @@ class ClockSampler:
                 "reasons": sorted(reasons)}
 
 
-def cpu_reference_rate(n_sample, n_ref, repeats=1):
-    """Reference CPU formulation (evaluation_metrics.py:85-121 / :35-45 restated in oracle.torch_ref) on a bounded
-    sample of the workload: n_sample x n_ref cloud pairs of 2048 points, batch_size 50 as in the README's test."""
-    import torch
+_CPU_KIND = None
+
+
+def _cpu_pairwise_cd():
+    """(function, kind): the CD half of the reference's _pairwise_EMD_CD_ loop (evaluation_metrics.py:85-121).  Its EMD half is
+    CUDA-only, so the loop is the restated one (oracle.torch_ref.pairwise_cd); when the reference tree is staged
+    (baseline/_ref/PDGN) the distance function inside it is the reference's OWN distChamfer (:35-45) => kind "reference",
+    otherwise the restated one, pinned bit-for-bit by tests/golden => kind "port"."""
+    global _CPU_KIND
     from oracle import torch_ref
+    fn, kind = torch_ref.pairwise_cd, "port"
+    try:
+        from oracle import ref_tree
+        if ref_tree.available():
+            own = ref_tree.load_reference().evaluation_metrics.distChamfer
+
+            def fn(sample_pcs, ref_pcs, batch_size, _loop=torch_ref.pairwise_cd):
+                saved = torch_ref.dist_chamfer
+                torch_ref.dist_chamfer = own
+                try:
+                    return _loop(sample_pcs, ref_pcs, batch_size)
+                finally:
+                    torch_ref.dist_chamfer = saved
+            kind = "reference"
+    except Exception:
+        fn, kind = torch_ref.pairwise_cd, "port"
+    _CPU_KIND = kind
+    return fn, kind
+
+
+def cpu_reference_rate(n_sample, n_ref, repeats=1):
+    """Reference CPU formulation on a bounded sample of the workload: n_sample x n_ref cloud pairs of 2048 points,
+    batch_size 50 as in the README's test, all host threads."""
+    import torch
     torch.set_num_threads(os.cpu_count() or 1)
+    pairwise_cd, _ = _cpu_pairwise_cd()
     smp = make_clouds(0, n_sample)
     ref = make_clouds(1, n_ref)
-    torch_ref.pairwise_cd(smp[:1], ref[: min(n_ref, 10)], 50)  # warm-up (MKL init, page-in)
+    pairwise_cd(smp[:1], ref[: min(n_ref, 10)], 50)  # warm-up (MKL init, page-in)
     t0 = time.perf_counter()
     for _ in range(repeats):
-        torch_ref.pairwise_cd(smp, ref, 50)
+        pairwise_cd(smp, ref, 50)
     dt = (time.perf_counter() - t0) / repeats
     return n_sample * n_ref / dt, dt
 
@@ -150,10 +187,10 @@ def run_reference(args, rank):
         "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": 1e3 * sum(times) / args.steps, "higher_is_better": True, "scaling": "strong",
         "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": WORKLOAD, "note": "reference CPU formulation (torch bmm Gram form + min, distChamfer loop) restated in "
-                   "oracle/torch_ref.py and pinned bit-exactly to the reference's own code by tests/golden; the Python reference itself "
-                   "cannot travel to the GPU box"},
-        "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
+        "config": {"workload": WORKLOAD, "note": "reference CPU formulation (torch bmm Gram form + min, distChamfer loop): the reference's own "
+                   "distChamfer from the staged tree baseline/_ref/PDGN inside the CD half of its pairwise loop (kind 'reference'), or the "
+                   "restatement in oracle/torch_ref.py pinned bit-exactly by tests/golden when the tree is not staged (kind 'port')"},
+        "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": _CPU_KIND or "port", "sample": sample},
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
@@ -210,10 +247,10 @@ def main():
         return all_cd
 
     def step_e2e():
-        a = smp_h.to(dev, non_blocking=True)
-        b = ref_h.to(dev, non_blocking=True)
-        all_cd, _ = em._pairwise_EMD_CD_(a, b, 50)
-        return all_cd.cpu()  # D2H of the step's result (synchronises)
+        # pinned HOST tensors straight into the public API: it copies what this rank's tile needs (everything at N=1, its
+        # rows + columns under torchrun) and returns the full matrix on the device; .cpu() is the D2H of the step's result
+        all_cd, _ = em._pairwise_EMD_CD_(smp_h, ref_h, 50)
+        return all_cd.cpu()
 
     def sync_all():
         torch.cuda.synchronize()
@@ -268,6 +305,14 @@ def main():
     torch.cuda.synchronize()
     kernel_ms = k0.elapsed_time(k1) / kreps
 
+    # ---- side measurements every rank takes part in (collectives inside)
+    extras_all = {}
+    if not args.no_extras:
+        if world == 8 or os.environ.get("PDGN_BENCH_CFG5_CD"):
+            extras_all["cd_4096x4096"] = bench_cfg5_cd(dev, em, dist, world, sync_all)
+        extras_all["eval_emd"] = bench_eval_emd(dev, em, dist, world, sync_all, smp_h, ref_h, nc)
+        os.environ["PDGN_B200_SKIP_EMD"] = "1"
+
     if rank != 0:
         if world > 1:
             dist.barrier()
@@ -309,8 +354,9 @@ def main():
                    "clouds": [nc, nc], "points_per_cloud": N_PTS, "partition": "%dx%d rank grid, all_gather of scalars" % pdist.rank_grid(world),
                    "l2": "256 MiB memset between steps (inside the timed region, ~0.05 ms)"},
         "e2e": {"value": e2e_value, "unit": UNIT, "ms_per_step": ms_e2e / args.steps,
-                "h2d_bytes_per_step": 2 * nc * N_PTS * 3 * 4, "d2h_bytes_per_step": nc * nc * 4,
-                "api": "pdgn_b200.evaluation_metrics._pairwise_EMD_CD_ (PDGN_B200_SKIP_EMD=1: CD half) on pinned host tensors (.to(device) + .cpu())"},
+                "h2d_bytes_per_step": world * ((rows[1] - rows[0]) + (cols[1] - cols[0])) * N_PTS * 3 * 4, "d2h_bytes_per_step": nc * nc * 4,
+                "h2d_note": "summed over ranks: each rank copies only the rows + columns of its tile",
+                "api": "pdgn_b200.evaluation_metrics._pairwise_EMD_CD_(pinned host tensors) (PDGN_B200_SKIP_EMD=1: CD half) + .cpu()"},
         "gpu_launches": 3 * args.steps,
         "roofline": roofline, "clocks": clocks,
     }
@@ -318,7 +364,11 @@ def main():
         line["knnquery"] = bench_knn(dev, lanes, sm_max_mhz)
         line["gathers"] = bench_gathers(dev, float(peaks.get("hbm_gbs") or 6650.0), "measured" if peaks.get("hbm_gbs") else "fallback")
         line["emd"] = bench_emd(dev)
+        line["cfg5"] = dict(_guard(bench_cfg5_knn, dev, lanes, sm_max_mhz), **{k: v for k, v in extras_all.items() if k == "cd_4096x4096"})
+        line["eval_emd"] = extras_all.get("eval_emd")
+        line["cfg3"] = _guard(bench_cfg3, dev)
         if world == 1:
+            line["reference_gpu"] = _guard(bench_reference_gpu, dev, value)
             n_s, n_r = 24, 50  # ~10 s of host work: a bounded sample of the 1000 x 1000 workload
             rate, dt = cpu_reference_rate(n_s, n_r)
             line["cpu_baseline"] = {"value": rate, "unit": UNIT, "cores": os.cpu_count() or 1, "kind": "port", "seconds": dt,
@@ -420,6 +470,244 @@ def bench_gathers(dev, hbm_gbs, src):
     res["interp_c256"] = {"fwd_ms": f_ms, "fwd_gbs": nbytes / (f_ms * 1e-3) / 1e9, "fwd_frac": nbytes / (f_ms * 1e-3) / 1e9 / hbm_gbs,
                           "bwd_ms": b_ms, "bwd_gbs": nbytes / (b_ms * 1e-3) / 1e9, "bwd_frac": nbytes / (b_ms * 1e-3) / 1e9 / hbm_gbs,
                           "algorithmic_mb": nbytes / 1e6}
+    return res
+
+
+def _guard(fn, *a):
+    """A side measurement must never take the headline line down with it."""
+    try:
+        return fn(*a)
+    except Exception as e:  # noqa: BLE001
+        return {"error": "%s: %s" % (type(e).__name__, str(e)[:300])}
+
+
+def bench_cfg5_knn(dev, lanes, sm_max_mhz):
+    """BASELINE configs[4], kNN half: knnquery k=32, self query, 16384-point clouds, B=8 and B=35."""
+    import numpy as np
+    import torch
+    from pdgn_b200 import ops
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
+    res = {}
+    for b in (8, 35):
+        rng = np.random.default_rng(b)
+        xyz = torch.from_numpy(rng.uniform(-1, 1, (b, 16384, 3)).astype(np.float32)).to(dev)
+        ms = _time_ms(lambda: ops.knn_xyz(32, xyz), 5, flush)
+        q = b * 16384
+        res["knn_k32_B%d_n16384" % b] = {"mqueries_per_s": q / (ms * 1e-3) / 1e6, "ms": ms,
+                                        "fp32_issue_frac": q * 16384.0 * FMA_PIPE_INSTR_PER_POINT_PAIR / (ms * 1e-3) / (lanes * sm_max_mhz * 1e6)}
+    return res
+
+
+def bench_cfg5_cd(dev, em, dist, world, sync_all):
+    """BASELINE configs[4], CD half: one 4096 x 4096 all-pairs matrix of 2048-point clouds over all ranks (device-resident
+    inputs, all_gather of the scalars inside; 1 warm-up + 2 timed steps; max over ranks)."""
+    import torch
+    try:
+        n = int(os.environ.get("PDGN_BENCH_CFG5_CLOUDS", "4096"))
+        a, b = make_clouds(2, n).to(dev), make_clouds(3, n).to(dev)
+        em._pairwise_EMD_CD_(a, b, 50)
+        sync_all()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(2):
+            out, _ = em._pairwise_EMD_CD_(a, b, 50)
+        e1.record()
+        sync_all()
+        ms = torch.tensor([e0.elapsed_time(e1) / 2], device=dev)
+        if world > 1:
+            dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+        ms = ms.item()
+        return {"clouds": [n, n], "ms": ms, "cloud_pairs_per_s": float(n) * n / (ms * 1e-3), "n_gpus": world,
+                "fp32_issue_frac_per_gpu": float(n) * n * POINT_PAIRS_PER_CLOUD_PAIR * FMA_PIPE_INSTR_PER_POINT_PAIR / (ms * 1e-3) /
+                (world * torch.cuda.get_device_properties(dev).multi_processor_count * 128 * 1965.0e6),
+                "checksum": float(out.double().sum().item())}
+    except Exception as e:  # noqa: BLE001
+        return {"error": "%s: %s" % (type(e).__name__, str(e)[:300])}
+
+
+def bench_eval_emd(dev, em, dist, world, sync_all, smp_h, ref_h, nc):
+    """What PDGNet_v2.test() actually waits for (PDGNet_v2.py:319): compute_all_metrics = three all-pairs CD matrices AND three
+    all-pairs approximate-EMD matrices, here from pinned HOST tensors with the H2D copies and a D2H of the 12 scalars inside
+    the timed region (one run, no repeat: it is seconds to a minute long)."""
+    import torch
+    try:
+        os.environ["PDGN_B200_SKIP_EMD"] = "0"
+        n = int(os.environ.get("PDGN_BENCH_EVAL_CLOUDS", str(nc)))
+        a, b = smp_h[:n], ref_h[:n]
+        em.compute_all_metrics(a[:16], b[:16], 50)      # warm-up: lazy module loads, NCCL channels
+        sync_all()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        res = em.compute_all_metrics(a, b, 50)
+        host = {k: float(v.item()) for k, v in res.items()}
+        e1.record()
+        sync_all()
+        ms = torch.tensor([e0.elapsed_time(e1)], device=dev)
+        if world > 1:
+            dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+        sec = ms.item() * 1e-3
+        return {"clouds": [n, n], "seconds": sec, "cloud_pairs_per_s_cd_and_emd": 3.0 * n * n / sec, "n_gpus": world, "keys": len(host),
+                "h2d_bytes": 2 * n * N_PTS * 3 * 4, "reference_says": "'may take about 2 hours' for the test phase (README.md:47)",
+                "mmd_cd": host.get("lgan_mmd-CD"), "mmd_emd": host.get("lgan_mmd-EMD")}
+    except Exception as e:  # noqa: BLE001
+        return {"error": "%s: %s" % (type(e).__name__, str(e)[:300])}
+    finally:
+        os.environ["PDGN_B200_SKIP_EMD"] = "1"
+
+
+def _ev_ms(fn, reps=5, warm=2):
+    import torch
+    for _ in range(warm):
+        fn()
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(reps):
+        fn()
+    e1.record()
+    torch.cuda.synchronize()
+    return e0.elapsed_time(e1) / reps
+
+
+def bench_cfg3(dev):
+    """BASELINE configs[2] (training path, B=35): the loss side of one G step -- six get_local_pair calls = 12 kNN + 12 grouping +
+    12 ChamferLoss problems (PDGNet_v2.py:232-237) -- forward+backward through the op the drop-in installs, the generator's four
+    feature-space kNN stages (get_edge_features_xyz, k=10) forward+backward, and, when the reference tree is staged, one G step
+    of the reference's OWN PointGenerator + get_local_pair code run through the drop-in vs over the reference stack."""
+    import numpy as np
+    import torch
+    from pdgn_b200 import edge_features as ef
+    from pdgn_b200 import local_pair
+    B = 35
+    rng = np.random.default_rng(0)
+
+    def cloud(n):
+        v = rng.standard_normal((B, n, 3))
+        v /= np.linalg.norm(v, axis=-1, keepdims=True)
+        return torch.from_numpy(np.ascontiguousarray((0.5 * v).astype(np.float32).transpose(0, 2, 1))).to(dev)
+
+    pts = {n: cloud(n) for n in (256, 512, 1024, 2048)}
+    sizes = [(256, 512), (256, 1024), (256, 2048), (512, 1024), (512, 2048), (1024, 2048)]
+
+    def loss_side(backward):
+        leaves = {n: p.clone().requires_grad_(backward) for n, p in pts.items()}
+        total = 0
+        for m_, n_ in sizes:
+            a, b = local_pair.get_local_pair(leaves[m_], leaves[n_])
+            total = total + a + b
+        if backward:
+            total.backward()
+        return total
+
+    res = {"batch": B, "loss_side_fwd_ms": _ev_ms(lambda: loss_side(False)), "loss_side_fwd_bwd_ms": _ev_ms(lambda: loss_side(True))}
+    stages = {}
+    for c, n in [(32, 128), (64, 256), (128, 512), (256, 1024)]:
+        x = torch.randn(B, c, n, device=dev)
+        pc = torch.rand(B, 3, n, device=dev) * 2 - 1
+
+        def stage():
+            xr, pr = x.clone().requires_grad_(True), pc.clone().requires_grad_(True)
+            e_fea, e_xyz = ef.get_edge_features_xyz(xr, pr, 10)
+            (e_fea.sum() + e_xyz.sum()).backward()
+
+        stages["C%d_N%d" % (c, n)] = _ev_ms(stage)
+    res["edge_feature_stage_fwd_bwd_ms"] = stages
+    try:
+        from oracle import ref_tree
+        if not ref_tree.available():
+            raise RuntimeError("reference tree not staged")
+        ref = ref_tree.load_reference()
+        drop = ref_tree.load_dropin()
+        torch.manual_seed(0)
+        g_ref = ref.model.PointGenerator(2048, 20).to(dev).train()
+        g_drop = drop.PointGenerator(2048, 20).to(dev).train()
+        g_drop.load_state_dict(g_ref.state_dict())
+        z = torch.randn(B, 128, device=dev) * 0.2
+        t_ref = ref_tree.bare_trainer(ref.model, ref.pointops.Gen_QueryAndGroupXYZ(radius=None, nsample=20, use_xyz=False), ref.chamfer_loss.ChamferLoss())
+        t_drop = ref_tree.bare_trainer(drop, drop.pointops.Gen_QueryAndGroupXYZ(radius=None, nsample=20, use_xyz=False), drop.chamfer_loss.ChamferLoss())
+
+        def g_step(gen, trainer):
+            gen.zero_grad(set_to_none=True)
+            p1, p2, p3, p4 = gen(z)
+            sim = 0.0
+            for a, b in ((p1, p2), (p1, p3), (p1, p4), (p2, p3), (p2, p4), (p3, p4)):
+                mu, cov = trainer.get_local_pair(a, b)
+                sim = sim + mu + cov
+            (0.1 * sim).backward()
+
+        res["generator_step_ms"] = _ev_ms(lambda: g_step(g_drop, t_drop), reps=3, warm=2)
+        res["generator_step_reference_stack_ms"] = _ev_ms(lambda: g_step(g_ref, t_ref), reps=2, warm=1)
+        res["generator_step_note"] = ("the reference's own PointGenerator.forward + get_local_pair x6 + backward (PDGNet_v2.py:228-255 without the "
+                                      "discriminators), batch 35, same weights: through pdgn_b200.dropin vs over the reference's torch "
+                                      "get_edge_features + recompiled pointops kernels + torch Gram ChamferLoss on this GPU")
+    except Exception as e:  # noqa: BLE001
+        res["generator_step_ms"] = None
+        res["generator_step_note"] = "not measured: %s" % str(e)[:200]
+    return res
+
+
+def bench_reference_gpu(dev, our_pairs_per_s):
+    """'Reference on B200' (SURVEY.md 8d): the reference's two ways of filling the CD matrix, on THIS GPU, on a bounded sample
+    of the 1000 x 1000 workload (10 generated clouds x all 1000 references, batch_size 50 as in README's test):
+      torch_gram   -- its default path: torch bmm Gram-form distChamfer inside the Python double loop (evaluation_metrics.py:85-121)
+      nndistance   -- accelerated_cd=True: the NNDistance kernel (nndistance.cu:2-128) recompiled for sm_100a, same loop
+    and the reference's real _pairwise_EMD_CD_ (CD + EMD) on 2 x 100 pairs next to ours with EMD on."""
+    import torch
+    from oracle import ref_kernels, torch_ref
+    if not ref_kernels.available():
+        return {"unavailable": "oracle/_ref/libpdgn_ref.so not built"}
+    n_s, n_r = 10, N_CLOUDS
+    smp, ref = make_clouds(0, n_s).to(dev), make_clouds(1, n_r).to(dev)
+    res = {"sample": "%d x %d cloud pairs of 2048 points, batch_size 50" % (n_s, n_r)}
+
+    def wall(fn, reps):
+        fn()
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        for _ in range(reps):
+            fn()
+        torch.cuda.synchronize()
+        return (time.perf_counter() - t0) / reps
+
+    dist_fn = torch_ref.dist_chamfer
+    kind = "port"
+    try:
+        from oracle import ref_tree
+        if ref_tree.available():
+            rmod = ref_tree.load_reference().evaluation_metrics
+            dist_fn, kind = rmod.distChamfer, "reference"
+    except Exception:  # noqa: BLE001
+        rmod = None
+
+    def loop(dfn):
+        rows = []
+        for s in range(n_s):
+            parts = []
+            for r0 in range(0, n_r, 50):
+                rb = ref[r0:r0 + 50]
+                rep = smp[s].view(1, -1, 3).expand(rb.size(0), -1, -1).contiguous()
+                dl, dr = dfn(rep, rb)
+                parts.append((dl.mean(dim=1) + dr.mean(dim=1)).view(1, -1))
+            rows.append(torch.cat(parts, dim=1))
+        return torch.cat(rows, dim=0)
+
+    def nnd(a, b):
+        d1, _, d2, _ = ref_kernels.nndistance(a, b)
+        return d1, d2
+
+    t = wall(lambda: loop(dist_fn), 2)
+    res["torch_gram"] = {"cloud_pairs_per_s": n_s * n_r / t, "seconds": t, "kind": kind, "ours_over_it": our_pairs_per_s / (n_s * n_r / t)}
+    t = wall(lambda: loop(nnd), 2)
+    res["nndistance"] = {"cloud_pairs_per_s": n_s * n_r / t, "seconds": t, "kind": "reference", "ours_over_it": our_pairs_per_s / (n_s * n_r / t)}
+    if kind == "reference":
+        from pdgn_b200 import ops
+        a, b = smp[:2].contiguous(), ref[:100].contiguous()
+        t = wall(lambda: rmod._pairwise_EMD_CD_(a, b, 50, accelerated_cd=False), 1)
+        ours = make_clouds(0, 148).to(dev), make_clouds(1, 148).to(dev)
+        t_o = wall(lambda: (ops.cd_allpairs(*ours), ops.emd_allpairs(*ours)), 1)
+        res["pairwise_emd_cd"] = {"reference_cloud_pairs_per_s": 200 / t, "reference_sample": "2 x 100 pairs (the function PDGNet_v2.test() "
+                                  "reaches through compute_all_metrics, CD + EMD)", "ours_cloud_pairs_per_s": 148 * 148 / t_o,
+                                  "ours_sample": "148 x 148 pairs, CD + EMD", "ours_over_it": (148 * 148 / t_o) / (200 / t)}
     return res
 
 

@@ -12,6 +12,9 @@
  *     entry point synchronises the host, allocates device memory or exits the process;
  *   - return value: 0 on success, PDGN_ERR_* (negative) for argument errors, or a positive cudaError_t
  *     from the launch.  pdgn_error_string() turns either into text.
+ *   - environment: PDGN_B200_VERIFY=1 range-checks every index tensor before it is used (one extra kernel and a stream
+ *     synchronisation per gather call; PDGN_ERR_INDEX on failure).  Every entry point opens an NVTX range of its own name.
+ *     Kernel-variant tuning hooks are inert unless PDGN_B200_TUNE=1.
  */
 #ifndef PDGN_B200_H
 #define PDGN_B200_H
@@ -29,6 +32,7 @@ extern "C" {
 #define PDGN_ERR_BAD_ARG (-1)      /* null pointer / negative size */
 #define PDGN_ERR_UNSUPPORTED (-2)  /* size outside what the kernels implement (stated per function) */
 #define PDGN_ERR_WORKSPACE (-3)    /* workspace too small */
+#define PDGN_ERR_INDEX (-4)        /* PDGN_B200_VERIFY=1 only: an index tensor holds a value outside [0, n) */
 
 int pdgn_abi_version(void);
 const char *pdgn_error_string(int code);

@@ -7,7 +7,7 @@ from concurrent.futures import ThreadPoolExecutor
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 SO = os.path.join(HERE, "libpdgn_b200.so")
-SOURCES = ["api.cu", "knn_xyz.cu", "gather.cu", "chamfer.cu", "cd_allpairs.cu", "knn_feat.cu", "emd.cu", "local_stats.cu", "local_pair.cu"]
+SOURCES = ["api.cu", "knn_xyz.cu", "gather.cu", "chamfer.cu", "cd_allpairs.cu", "knn_feat.cu", "emd.cu", "local_stats.cu", "local_pair.cu", "verify.cu"]
 NVCC_FLAGS = ["-O3", "-std=c++17", "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-Xcompiler", "-fPIC"]
 
 
@@ -39,7 +39,7 @@ def build(force=False, verbose=False):
 
     with ThreadPoolExecutor(max_workers=min(8, len(SOURCES))) as ex:
         objs = list(ex.map(cc, SOURCES))
-    r = subprocess.run([nvcc, "-shared", "-gencode", "arch=compute_100a,code=sm_100a", "-o", SO] + objs, capture_output=True, text=True)
+    r = subprocess.run([nvcc, "-shared", "-gencode", "arch=compute_100a,code=sm_100a", "-o", SO] + objs + ["-ldl"], capture_output=True, text=True)
     if r.returncode != 0:
         raise RuntimeError("link failed:\n" + r.stderr)
     return SO

@@ -72,6 +72,7 @@ extern "C" size_t pdgn_cd_allpairs_workspace(int na, int nb, int npts) {
 extern "C" int pdgn_cd_allpairs(const float* A, const float* B, int na, int nb, int npts, int row0, int row1, int col0,
                                 int col1, float* out, long long ld_out, void* workspace, size_t workspace_bytes,
                                 void* stream) {
+    PDGN_RANGE("pdgn_cd_allpairs");
     if (na < 0 || nb < 0 || npts <= 0) return PDGN_ERR_BAD_ARG;
     if (row0 < 0 || row1 > na || row0 > row1 || col0 < 0 || col1 > nb || col0 > col1) return PDGN_ERR_BAD_ARG;
     if (npts > 16384) return PDGN_ERR_UNSUPPORTED;
@@ -104,7 +105,7 @@ extern "C" int pdgn_cd_allpairs(const float* A, const float* B, int na, int nb, 
     if (spairs > 65535) return PDGN_ERR_UNSUPPORTED;
     // enough CTAs that the last partial wave is a small fraction of the run; each CTA walks `rstrip` B clouds
     static const int waves = [] {  // tuning hook
-        const char* e = getenv("PDGN_CD_WAVES");
+        const char* e = tune_env("PDGN_CD_WAVES");
         const int v = e ? atoi(e) : 0;
         return v > 0 ? v : 64;
     }();
@@ -115,7 +116,7 @@ extern "C" int pdgn_cd_allpairs(const float* A, const float* B, int na, int nb, 
     const int rstrip = (ncols + strips - 1) / strips;
     strips = (ncols + rstrip - 1) / rstrip;
     const dim3 grid(strips, spairs);
-    static const bool force_big = getenv("PDGN_CD_ATOMIC_COLMIN") != nullptr;  // tuning hook: the shared-atomic variant for every size
+    static const bool force_big = tune_env("PDGN_CD_ATOMIC_COLMIN") != nullptr;  // tuning hook: the shared-atomic variant for every size
     int rc;
     if (npts <= CD_R * CD_HALF && !force_big)
         rc = cd_launch<CD_VARIANT>(sym, grid, cd_smem_bytes<CD_NH, CD_VARIANT>(npad), st, PA, PB, nrows, ncols, npts, npad, rstrip, out, ld_out);
@@ -131,6 +132,7 @@ extern "C" int pdgn_cd_allpairs(const float* A, const float* B, int na, int nb, 
 
 extern "C" int pdgn_cd_allpairs_host(const float* A_host, const float* B_host, int na, int nb, int npts, int row0, int row1,
                                      int col0, int col1, float* out_host, long long ld_out, void* stream) {
+    PDGN_RANGE("pdgn_cd_allpairs_host");
     if (!A_host || !B_host || !out_host || na < 0 || nb < 0 || npts <= 0) return PDGN_ERR_BAD_ARG;
     if (row0 < 0 || row1 > na || row0 > row1 || col0 < 0 || col1 > nb || col0 > col1) return PDGN_ERR_BAD_ARG;
     const int nrows = row1 - row0, ncols = col1 - col0;

@@ -185,6 +185,7 @@ using namespace pdgn;
 
 extern "C" int pdgn_chamfer_min(const float* x, const float* y, int b, int nx, int ny, int d, float* min_xy, int* arg_xy,
                                 float* min_yx, int* arg_yx, void* stream) {
+    PDGN_RANGE("pdgn_chamfer_min");
     if (b < 0 || nx < 0 || ny < 0) return PDGN_ERR_BAD_ARG;
     if (d < 1 || d > CH_DMAX || b > 65535) return PDGN_ERR_UNSUPPORTED;
     if ((!min_xy && arg_xy) || (!min_yx && arg_yx)) return PDGN_ERR_BAD_ARG;
@@ -201,11 +202,14 @@ extern "C" int pdgn_chamfer_min(const float* x, const float* y, int b, int nx, i
 
 extern "C" int pdgn_chamfer_bwd(const float* x, const float* y, int b, int nx, int ny, int d, const float* w_xy, const int* arg_xy,
                                 const float* w_yx, const int* arg_yx, float* grad_x, float* grad_y, void* stream) {
+    PDGN_RANGE("pdgn_chamfer_bwd");
     if (!x || !y || !grad_x || !grad_y || b < 0 || nx < 0 || ny < 0 || d < 1) return PDGN_ERR_BAD_ARG;
     if ((w_xy == nullptr) != (arg_xy == nullptr) || (w_yx == nullptr) != (arg_yx == nullptr)) return PDGN_ERR_BAD_ARG;
     if (b > 65535) return PDGN_ERR_UNSUPPORTED;
     if (b == 0 || nx == 0 || ny == 0) return PDGN_OK;
     cudaStream_t st = (cudaStream_t)stream;
+    if (arg_xy) PDGN_VERIFY_IDX32(arg_xy, (size_t)b * nx, ny, st);
+    if (arg_yx) PDGN_VERIFY_IDX32(arg_yx, (size_t)b * ny, nx, st);
     if (w_xy) {
         chamfer_bwd_kernel<<<dim3((nx + 255) / 256, b), 256, 0, st>>>(x, y, nx, ny, d, w_xy, arg_xy, grad_x, grad_y);
         PDGN_CHECK_LAUNCH();

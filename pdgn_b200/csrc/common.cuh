@@ -1,7 +1,9 @@
 // common.cuh -- shared device helpers for libpdgn_b200 (sm_100a only).
 #pragma once
 #include <cuda_runtime.h>
+#include <nvtx3/nvToolsExt.h>
 #include <stdint.h>
+#include <stdlib.h>
 #include "../../include/pdgn_b200.h"
 
 #if defined(__CUDA_ARCH__) && (__CUDA_ARCH__ < 1000)
@@ -75,6 +77,46 @@ __device__ __forceinline__ void bulk_g2s(void* dst_smem, const void* src_gmem, u
 __device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 
 }  // namespace pdgn
+
+namespace pdgn {
+// NVTX range around every C-ABI entry point (host side; a no-op function-pointer test unless a profiler is attached).
+struct NvtxRange {
+    explicit NvtxRange(const char* name) { nvtxRangePushA(name); }
+    ~NvtxRange() { nvtxRangePop(); }
+    NvtxRange(const NvtxRange&) = delete;
+    NvtxRange& operator=(const NvtxRange&) = delete;
+};
+// Tuning hooks (kernel-variant overrides used by tools/ and the ablation profiles) are read only when PDGN_B200_TUNE=1:
+// a stray environment variable cannot change what the shipped library computes with.
+inline const char* tune_env(const char* name) {
+    static const bool on = [] { const char* e = getenv("PDGN_B200_TUNE"); return e && e[0] == '1'; }();
+    return on ? getenv(name) : nullptr;
+}
+// PDGN_B200_VERIFY=1: every gather / scatter entry point first checks its index tensor against [0, n) (one extra kernel and
+// a stream synchronisation per call -- a debugging mode; the reference never checks, grouping_cuda_kernel.cu:70-71).
+inline bool verify_on() {
+    static const bool on = [] { const char* e = getenv("PDGN_B200_VERIFY"); return e && e[0] == '1'; }();
+    return on;
+}
+int verify_idx32(const int* idx, size_t count, int n, cudaStream_t st);      // PDGN_OK or PDGN_ERR_INDEX (verify.cu)
+int verify_idx64(const int64_t* idx, size_t count, int n, cudaStream_t st);
+}  // namespace pdgn
+
+#define PDGN_RANGE(name) ::pdgn::NvtxRange pdgn_nvtx_range__(name)
+#define PDGN_VERIFY_IDX32(idx, count, n, st)                                         \
+    do {                                                                             \
+        if (::pdgn::verify_on()) {                                                   \
+            const int v__ = ::pdgn::verify_idx32((idx), (size_t)(count), (n), (st)); \
+            if (v__ != PDGN_OK) return v__;                                          \
+        }                                                                            \
+    } while (0)
+#define PDGN_VERIFY_IDX64(idx, count, n, st)                                         \
+    do {                                                                             \
+        if (::pdgn::verify_on()) {                                                   \
+            const int v__ = ::pdgn::verify_idx64((idx), (size_t)(count), (n), (st)); \
+            if (v__ != PDGN_OK) return v__;                                          \
+        }                                                                            \
+    } while (0)
 
 #define PDGN_CHECK_LAUNCH()                          \
     do {                                             \

@@ -352,6 +352,7 @@ extern "C" size_t pdgn_emd_allpairs_workspace(int na, int nb, int n, int m) {
 
 extern "C" int pdgn_emd_allpairs(const float* A, const float* B, int na, int nb, int n, int m, int row0, int row1, int col0,
                                  int col1, float* out, long long ld_out, void* workspace, size_t workspace_bytes, void* stream) {
+    PDGN_RANGE("pdgn_emd_allpairs");
     if (na < 0 || nb < 0 || n <= 0 || m <= 0) return PDGN_ERR_BAD_ARG;
     if (row0 < 0 || row1 > na || row0 > row1 || col0 < 0 || col1 > nb || col0 > col1) return PDGN_ERR_BAD_ARG;
     if (n > EM_MAX || m > EM_MAX) return PDGN_ERR_UNSUPPORTED;
@@ -387,6 +388,7 @@ extern "C" size_t pdgn_emd_paired_workspace(int b, int n, int m) { return pdgn_e
 
 extern "C" int pdgn_emd_paired(const float* A, const float* B, int b, int n, int m, float* out, void* workspace,
                                size_t workspace_bytes, void* stream) {
+    PDGN_RANGE("pdgn_emd_paired");
     if (b < 0 || n <= 0 || m <= 0) return PDGN_ERR_BAD_ARG;
     if (n > EM_MAX || m > EM_MAX) return PDGN_ERR_UNSUPPORTED;
     if (b == 0) return PDGN_OK;

@@ -81,7 +81,7 @@ __global__ void __launch_bounds__(GT) group_bwd_kernel(const float* __restrict__
 static int gs_row_bytes() {  // shared budget for staged rows per CTA (tuning hook: PDGN_GS_ROW_KB)
     static int v = 0;
     if (v == 0) {
-        const char* e = getenv("PDGN_GS_ROW_KB");
+        const char* e = tune_env("PDGN_GS_ROW_KB");
         v = (e ? atoi(e) : 16) * 1024;  // 16 KB: 84.5 % of HBM at the C=256 stress shape (64 KB: 75 %), profiles/r01_gather_tune.txt
     }
     return v;
@@ -699,10 +699,12 @@ using namespace pdgn;
     if (!(__VA_ARGS__)) return PDGN_ERR_BAD_ARG
 
 extern "C" int pdgn_group_fwd(const float* points, const int* idx, int b, int c, int n, int m, int k, float* out, void* stream) {
+    PDGN_RANGE("pdgn_group_fwd");
     PDGN_GATHER_ARGS_OK(b >= 0 && c >= 0 && n >= 0 && m >= 0 && k >= 0);
     const long long mk = (long long)m * k;
     if (b == 0 || c == 0 || mk == 0) return PDGN_OK;  // empty output
     PDGN_GATHER_ARGS_OK(points && idx && out && n > 0);
+    PDGN_VERIFY_IDX32(idx, (size_t)b * m * k, n, (cudaStream_t)stream);
     if (mk > 0x7fffffffLL || b > 65535) return PDGN_ERR_UNSUPPORTED;
     const bool vec = (mk % 4 == 0) && ((reinterpret_cast<uintptr_t>(out) | reinterpret_cast<uintptr_t>(idx)) % 16 == 0);
     if (vec && c >= 8 && (size_t)n * 4 * 4 <= GS_ROW_BYTES) {
@@ -745,10 +747,12 @@ extern "C" size_t pdgn_group_bwd_workspace(int b, int n, int m, int k) {
 
 extern "C" int pdgn_group_bwd_ws(const float* grad_out, const int* idx, int b, int c, int n, int m, int k, float* grad_points,
                                  void* workspace, size_t workspace_bytes, void* stream) {
+    PDGN_RANGE("pdgn_group_bwd_ws");
     PDGN_GATHER_ARGS_OK(b >= 0 && c >= 0 && n >= 0 && m >= 0 && k >= 0);
     const long long mk = (long long)m * k;
     if (b == 0 || c == 0 || mk == 0) return PDGN_OK;  // nothing to add
     PDGN_GATHER_ARGS_OK(grad_out && idx && grad_points && n > 0);
+    PDGN_VERIFY_IDX32(idx, (size_t)b * m * k, n, (cudaStream_t)stream);
     if (mk > 0x7fffffffLL || b > 65535) return PDGN_ERR_UNSUPPORTED;
     const size_t row_bytes = (size_t)mk * 4;
     const size_t csr_smem = ((size_t)2 * n + 32) * sizeof(int);
@@ -776,10 +780,12 @@ extern "C" int pdgn_group_bwd_ws(const float* grad_out, const int* idx, int b, i
 
 extern "C" int pdgn_group_bwd(const float* grad_out, const int* idx, int b, int c, int n, int m, int k, float* grad_points,
                               void* stream) {
+    PDGN_RANGE("pdgn_group_bwd");
     PDGN_GATHER_ARGS_OK(b >= 0 && c >= 0 && n >= 0 && m >= 0 && k >= 0);
     const long long mk = (long long)m * k;
     if (b == 0 || c == 0 || mk == 0) return PDGN_OK;  // nothing to add
     PDGN_GATHER_ARGS_OK(grad_out && idx && grad_points && n > 0);
+    PDGN_VERIFY_IDX32(idx, (size_t)b * m * k, n, (cudaStream_t)stream);
     if (mk > 0x7fffffffLL || b > 65535) return PDGN_ERR_UNSUPPORTED;
     const bool vec = (mk % 4 == 0) && ((reinterpret_cast<uintptr_t>(grad_out) | reinterpret_cast<uintptr_t>(idx)) % 16 == 0);
     const long long per = vec ? 4 : 1;
@@ -795,9 +801,11 @@ extern "C" int pdgn_group_bwd(const float* grad_out, const int* idx, int b, int 
 
 extern "C" int pdgn_interp_fwd(const float* points, const int* idx, const float* weight, int b, int c, int m, int n, float* out,
                                void* stream) {
+    PDGN_RANGE("pdgn_interp_fwd");
     PDGN_GATHER_ARGS_OK(b >= 0 && c >= 0 && m >= 0 && n >= 0);
     if (b == 0 || c == 0 || n == 0) return PDGN_OK;
     PDGN_GATHER_ARGS_OK(points && idx && weight && out && m > 0);
+    PDGN_VERIFY_IDX32(idx, (size_t)b * n * 3, m, (cudaStream_t)stream);
     if (b > 65535) return PDGN_ERR_UNSUPPORTED;
     const bool vec = (n % 4 == 0) && ((reinterpret_cast<uintptr_t>(out) | reinterpret_cast<uintptr_t>(idx) |
                                        reinterpret_cast<uintptr_t>(weight)) % 16 == 0);
@@ -838,9 +846,11 @@ extern "C" size_t pdgn_interp_bwd_workspace(int b, int n, int m) {
 
 extern "C" int pdgn_interp_bwd_ws(const float* grad_out, const int* idx, const float* weight, int b, int c, int n, int m,
                                   float* grad_points, void* workspace, size_t workspace_bytes, void* stream) {
+    PDGN_RANGE("pdgn_interp_bwd_ws");
     PDGN_GATHER_ARGS_OK(b >= 0 && c >= 0 && m >= 0 && n >= 0);
     if (b == 0 || c == 0 || n == 0) return PDGN_OK;
     PDGN_GATHER_ARGS_OK(grad_out && idx && weight && grad_points && m > 0);
+    PDGN_VERIFY_IDX32(idx, (size_t)b * n * 3, m, (cudaStream_t)stream);
     if (b > 65535) return PDGN_ERR_UNSUPPORTED;
     const size_t csr_smem = ((size_t)2 * m + 32) * sizeof(int);
     int cc = PULL_CC;
@@ -864,9 +874,11 @@ extern "C" int pdgn_interp_bwd_ws(const float* grad_out, const int* idx, const f
 
 extern "C" int pdgn_interp_bwd(const float* grad_out, const int* idx, const float* weight, int b, int c, int n, int m,
                                float* grad_points, void* stream) {
+    PDGN_RANGE("pdgn_interp_bwd");
     PDGN_GATHER_ARGS_OK(b >= 0 && c >= 0 && m >= 0 && n >= 0);
     if (b == 0 || c == 0 || n == 0) return PDGN_OK;
     PDGN_GATHER_ARGS_OK(grad_out && idx && weight && grad_points && m > 0);
+    PDGN_VERIFY_IDX32(idx, (size_t)b * n * 3, m, (cudaStream_t)stream);
     if (b > 65535) return PDGN_ERR_UNSUPPORTED;
     const unsigned gx = (unsigned)((n + GT - 1) / GT);
     const int cpb = pick_cpb((long long)gx * b, c);
@@ -878,10 +890,12 @@ extern "C" int pdgn_interp_bwd(const float* grad_out, const int* idx, const floa
 }
 
 extern "C" int pdgn_edge_feat_fwd(const float* x, const int64_t* idx, int b, int c, int n, int k, float* ee, void* stream) {
+    PDGN_RANGE("pdgn_edge_feat_fwd");
     PDGN_GATHER_ARGS_OK(b >= 0 && c >= 0 && n >= 0 && k >= 0);
     const long long nk = (long long)n * k;
     if (b == 0 || c == 0 || nk == 0) return PDGN_OK;
     PDGN_GATHER_ARGS_OK(x && idx && ee);
+    PDGN_VERIFY_IDX64(idx, (size_t)b * n * k, n, (cudaStream_t)stream);
     if (b > 65535 || nk > 0x7fffffffLL) return PDGN_ERR_UNSUPPORTED;
     const bool vec = (nk % 4 == 0) && (reinterpret_cast<uintptr_t>(ee) % 16 == 0);
     const long long per = vec ? 4 : 1;
@@ -898,9 +912,11 @@ extern "C" int pdgn_edge_feat_fwd(const float* x, const int64_t* idx, int b, int
 
 extern "C" int pdgn_edge_feat_bwd(const float* grad_ee, const int64_t* idx, int b, int c, int n, int k, float* grad_x,
                                   void* stream) {
+    PDGN_RANGE("pdgn_edge_feat_bwd");
     PDGN_GATHER_ARGS_OK(b >= 0 && c >= 0 && n >= 0 && k >= 0);
     if (b == 0 || c == 0 || n == 0 || k == 0) return PDGN_OK;
     PDGN_GATHER_ARGS_OK(grad_ee && idx && grad_x);
+    PDGN_VERIFY_IDX64(idx, (size_t)b * n * k, n, (cudaStream_t)stream);
     if (b > 65535) return PDGN_ERR_UNSUPPORTED;
     const unsigned gx = (unsigned)((n + GT - 1) / GT);
     const int cpb = pick_cpb((long long)gx * b, c);
@@ -918,9 +934,11 @@ extern "C" size_t pdgn_edge_feat_bwd_workspace(int b, int n, int k) {
 
 extern "C" int pdgn_edge_feat_bwd_ws(const float* grad_ee, const int64_t* idx, int b, int c, int n, int k, float* grad_x,
                                      void* workspace, size_t workspace_bytes, void* stream) {
+    PDGN_RANGE("pdgn_edge_feat_bwd_ws");
     PDGN_GATHER_ARGS_OK(b >= 0 && c >= 0 && n >= 0 && k >= 0);
     if (b == 0 || c == 0 || n == 0 || k == 0) return PDGN_OK;
     PDGN_GATHER_ARGS_OK(grad_ee && idx && grad_x);
+    PDGN_VERIFY_IDX64(idx, (size_t)b * n * k, n, (cudaStream_t)stream);
     if (b > 65535) return PDGN_ERR_UNSUPPORTED;
     const long long nk = (long long)n * k;
     const size_t csr_smem = ((size_t)2 * n + 32) * sizeof(int);

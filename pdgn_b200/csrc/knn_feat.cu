@@ -102,6 +102,7 @@ __global__ void __launch_bounds__(FT) knn_feat_kernel(const float* __restrict__ 
 using namespace pdgn;
 
 extern "C" int pdgn_knn_feat(const float* x, int b, int c, int n, int k, int skip, int64_t* idx, float* dist2, void* stream) {
+    PDGN_RANGE("pdgn_knn_feat");
     if (!x || !idx || b < 0 || c < 1 || n < 0 || k < 1 || skip < 0) return PDGN_ERR_BAD_ARG;
     if (k + skip > 64 || b > 65535) return PDGN_ERR_UNSUPPORTED;
     if (k + skip > n) return PDGN_ERR_BAD_ARG;  // the reference's slice [1:k+1] would come up short

@@ -502,7 +502,7 @@ static int knn_dispatch(const float* xyz, const float* new_xyz, int b, int n, in
     int log2ss = 0, gsz = 0;
     // tiny k with few candidates: register-resident lists (every lane inserts ~k ln(n) times, which keeps the whole warp in
     // the divergent insertion path once n is in the hundreds: 22 instr/pair at n = 1024, so larger n goes to the select kernel)
-    static const bool force_smallk = getenv("PDGN_KNN_SMALLK") != nullptr;  // tuning hook
+    static const bool force_smallk = tune_env("PDGN_KNN_SMALLK") != nullptr;  // tuning hook
     if (k <= 4 && (n < 256 || force_smallk || !select_plan(n, k, 32, &log2ss, &gsz))) {
         switch (k) {
             case 1: return launch_smallk<1>(xyz, new_xyz, b, n, m, idx, dist2, st);
@@ -520,7 +520,7 @@ static int knn_dispatch(const float* xyz, const float* new_xyz, int b, int n, in
     const int width = (long long)((m + 511) / 512) * b >= want ? 16 : (long long)((m + 255) / 256) * b >= want ? 8
                     : (long long)((m + 127) / 128) * b >= want ? 4 : 2;
     // fewer than ~132 CTAs even at 8 / 4 / 2 query blocks per CTA: S = 2 / 4 / 4 slices per block instead of narrower CTAs
-    static const bool no_slices = getenv("PDGN_KNN_NOSLICES") != nullptr;  // tuning hook
+    static const bool no_slices = tune_env("PDGN_KNN_NOSLICES") != nullptr;  // tuning hook
 #define PDGN_KS_LAUNCH(G_)                                                                                        \
     do {                                                                                                          \
         const bool sliced = !no_slices && n <= KS_TILE && log2ss <= 4;                                            \
@@ -534,7 +534,7 @@ static int knn_dispatch(const float* xyz, const float* new_xyz, int b, int n, in
         if (width == 4) return launch_select<G_, 4>(xyz, new_xyz, b, n, m, k, log2ss, gsz, idx, dist2, st);       \
         return launch_select<G_, 2>(xyz, new_xyz, b, n, m, k, log2ss, gsz, idx, dist2, st);                       \
     } while (0)
-    static const bool wide_groups = getenv("PDGN_KNN_G32") == nullptr;  // tuning hook: PDGN_KNN_G32=1 keeps 32 groups
+    static const bool wide_groups = tune_env("PDGN_KNN_G32") == nullptr;  // tuning hook: PDGN_KNN_G32=1 keeps 32 groups
     if (k > 12 && k <= 24 && wide_groups && select_plan(n, k, 64, &log2ss, &gsz) && (n + (1 << log2ss) - 1) >> log2ss > 32 * gsz)
         PDGN_KS_LAUNCH(64);
     if (k <= 24 && select_plan(n, k, 32, &log2ss, &gsz)) PDGN_KS_LAUNCH(32);
@@ -553,6 +553,7 @@ static int knn_dispatch(const float* xyz, const float* new_xyz, int b, int n, in
 using namespace pdgn;
 
 extern "C" int pdgn_knn_xyz(const float* xyz, const float* new_xyz, int b, int n, int m, int k, int* idx, float* dist2, void* stream) {
+    PDGN_RANGE("pdgn_knn_xyz");
     if (b < 0 || n < 0 || m < 0 || k < 1) return PDGN_ERR_BAD_ARG;
     if (k > 128 || b > 65535) return PDGN_ERR_UNSUPPORTED;
     if (b == 0 || m == 0) return PDGN_OK;  // empty query set: nothing to write (pointers may be null)
@@ -562,6 +563,7 @@ extern "C" int pdgn_knn_xyz(const float* xyz, const float* new_xyz, int b, int n
 }
 
 extern "C" int pdgn_nn3(const float* unknown, const float* known, int b, int n, int m, float* dist2, int* idx, void* stream) {
+    PDGN_RANGE("pdgn_nn3");
     if (b < 0 || n < 0 || m < 0) return PDGN_ERR_BAD_ARG;
     if (b > 65535) return PDGN_ERR_UNSUPPORTED;
     if (b == 0 || n == 0) return PDGN_OK;

@@ -93,6 +93,7 @@ extern "C" size_t pdgn_local_pair_workspace(int b, int m, int n, int k) {
 
 extern "C" int pdgn_local_pair_fwd(const float* pt1, const float* pt2, int b, int m, int n, int k, float* out, void* workspace,
                                    size_t workspace_bytes, void* stream) {
+    PDGN_RANGE("pdgn_local_pair_fwd");
     if (b < 0 || m < 0 || n < 0 || k < 1) return PDGN_ERR_BAD_ARG;
     if (k > 64 || b > 65535) return PDGN_ERR_UNSUPPORTED;
     if (!out) return PDGN_ERR_BAD_ARG;
@@ -122,6 +123,7 @@ extern "C" int pdgn_local_pair_fwd(const float* pt1, const float* pt2, int b, in
 
 extern "C" int pdgn_local_pair_bwd(int b, int m, int n, int k, const float* grad_out, float* grad_pt1, float* grad_pt2,
                                    void* workspace, size_t workspace_bytes, void* stream) {
+    PDGN_RANGE("pdgn_local_pair_bwd");
     if (b <= 0 || m <= 0 || n <= 0 || k < 1 || !grad_out || !grad_pt1 || !grad_pt2) return PDGN_ERR_BAD_ARG;
     if (k > 64 || b > 65535) return PDGN_ERR_UNSUPPORTED;
     const LpLayout L = lp_layout(b, m, n, k);

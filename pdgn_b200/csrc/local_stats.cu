@@ -78,10 +78,12 @@ __global__ void __launch_bounds__(LS_T) local_stats_bwd_kernel(const float* __re
 using namespace pdgn;
 
 extern "C" int pdgn_local_stats_fwd(const float* xyz, const int* idx, int b, int n, int m, int k, float* mu, float* cov, void* stream) {
+    PDGN_RANGE("pdgn_local_stats_fwd");
     if (b < 0 || n < 0 || m < 0 || k < 1) return PDGN_ERR_BAD_ARG;
     if (k > LS_KMAX || b > 65535) return PDGN_ERR_UNSUPPORTED;
     if (b == 0 || m == 0) return PDGN_OK;
     if (!xyz || !idx || !mu || !cov || n == 0) return PDGN_ERR_BAD_ARG;
+    PDGN_VERIFY_IDX32(idx, (size_t)b * m * k, n, (cudaStream_t)stream);
     local_stats_fwd_kernel<<<dim3((m + LS_T - 1) / LS_T, b), LS_T, 0, (cudaStream_t)stream>>>(xyz, idx, n, m, k, mu, cov);
     PDGN_CHECK_LAUNCH();
     return PDGN_OK;
@@ -89,10 +91,12 @@ extern "C" int pdgn_local_stats_fwd(const float* xyz, const int* idx, int b, int
 
 extern "C" int pdgn_local_stats_bwd(const float* xyz, const int* idx, const float* mu, const float* grad_mu, const float* grad_cov,
                                     int b, int n, int m, int k, float* grad_xyz, void* stream) {
+    PDGN_RANGE("pdgn_local_stats_bwd");
     if (b < 0 || n < 0 || m < 0 || k < 1) return PDGN_ERR_BAD_ARG;
     if (k > LS_KMAX || b > 65535) return PDGN_ERR_UNSUPPORTED;
     if (b == 0 || m == 0) return PDGN_OK;
     if (!xyz || !idx || !mu || !grad_mu || !grad_cov || !grad_xyz || n == 0) return PDGN_ERR_BAD_ARG;
+    PDGN_VERIFY_IDX32(idx, (size_t)b * m * k, n, (cudaStream_t)stream);
     local_stats_bwd_kernel<<<dim3((m + LS_T - 1) / LS_T, b), LS_T, 0, (cudaStream_t)stream>>>(xyz, idx, mu, grad_mu, grad_cov, n, m, k,
                                                                                              grad_xyz);
     PDGN_CHECK_LAUNCH();

@@ -37,12 +37,20 @@ def tile_of(rank, world, n_rows, n_cols):
     return split(n_rows, pr, rank // pc), split(n_cols, pc, rank % pc)
 
 
-def assemble(tiles, world, n_rows, n_cols, like):
-    """Inverse of tile_of: paste the per-rank padded tiles (list of [max_r, max_c]) into the full matrix."""
-    full = like.new_empty((n_rows, n_cols))
-    for r in range(world):
-        (r0, r1), (c0, c1) = tile_of(r, world, n_rows, n_cols)
-        full[r0:r1, c0:c1] = tiles[r][: r1 - r0, : c1 - c0]
+def assemble(tiles, world, n_rows, n_cols, like=None):
+    """Inverse of tile_of: the per-rank padded tiles ([world, max_r, max_c], or a list of [max_r, max_c]) -> full matrix.
+    One strided copy when the grid divides the matrix evenly; otherwise two index_selects drop the padding."""
+    if isinstance(tiles, (list, tuple)):
+        tiles = torch.stack(list(tiles))
+    pr, pc = rank_grid(world)
+    mr, mc = tiles.shape[1], tiles.shape[2]
+    full = tiles.view(pr, pc, mr, mc).permute(0, 2, 1, 3).reshape(pr * mr, pc * mc)
+    if pr * mr != n_rows:
+        keep = torch.cat([torch.arange(*split(n_rows, pr, i)) - split(n_rows, pr, i)[0] + i * mr for i in range(pr)])
+        full = full.index_select(0, keep.to(full.device))
+    if pc * mc != n_cols:
+        keep = torch.cat([torch.arange(*split(n_cols, pc, i)) - split(n_cols, pc, i)[0] + i * mc for i in range(pc)])
+        full = full.index_select(1, keep.to(full.device))
     return full
 
 
@@ -71,6 +79,34 @@ def sym_plan(world, n, blocks_per_rank=4):
     return bounds, owner
 
 
+_SYM_MAPS = {}
+
+
+def _sym_maps(world, n, device):
+    """(bounds, owner, longest, src, dst, dst_mirror): flat gather/scatter indices that paste the all_gathered tile buffers of
+    sym_plan into the full [n, n] matrix (and its mirror image) with two index_puts instead of one copy per tile."""
+    key = (world, n, str(device))
+    if key not in _SYM_MAPS:
+        import numpy as np
+        bounds, owner = sym_plan(world, n)
+        area = lambda ij: (bounds[ij[0]][1] - bounds[ij[0]][0]) * (bounds[ij[1]][1] - bounds[ij[1]][0])
+        longest = max(1, max(sum(area(ij) for ij in tiles) for tiles in owner))
+        src, dst, msrc, mdst = [], [], [], []
+        for r in range(world):
+            at = r * longest
+            for ij in owner[r]:
+                (r0, r1), (c0, c1) = bounds[ij[0]], bounds[ij[1]]
+                rr, cc = np.meshgrid(np.arange(r0, r1), np.arange(c0, c1), indexing="ij")
+                pos = at + np.arange(rr.size)
+                src.append(pos); dst.append((rr * n + cc).reshape(-1))
+                if ij[0] != ij[1]:
+                    msrc.append(pos); mdst.append((cc * n + rr).reshape(-1))
+                at += rr.size
+        cat = lambda parts: torch.from_numpy(np.concatenate(parts) if parts else np.zeros(0, dtype=np.int64)).to(device)
+        _SYM_MAPS[key] = (bounds, owner, longest, cat(src), cat(dst), cat(msrc), cat(mdst))
+    return _SYM_MAPS[key]
+
+
 def pairwise_cd_symmetric(pcs, group=None, compute_tile=None):
     """Full [N, N] Chamfer matrix of a cloud set against itself on every rank, computing every unordered pair once."""
     world = dist_.get_world_size(group)
@@ -78,33 +114,29 @@ def pairwise_cd_symmetric(pcs, group=None, compute_tile=None):
     n = pcs.shape[0]
     if compute_tile is None:
         compute_tile = ops.cd_allpairs
-    bounds, owner = sym_plan(world, n)
+    bounds, owner, longest, src, dst, msrc, mdst = _sym_maps(world, n, pcs.device)
     area = lambda ij: (bounds[ij[0]][1] - bounds[ij[0]][0]) * (bounds[ij[1]][1] - bounds[ij[1]][0])
-    longest = max(sum(area(ij) for ij in tiles) for tiles in owner)
-    mine = pcs.new_zeros((max(longest, 1),))
+    mine = pcs.new_zeros((longest,))
     at = 0
     for ij in owner[rank]:
         rows, cols = bounds[ij[0]], bounds[ij[1]]
         if rows[1] > rows[0] and cols[1] > cols[0]:
             mine[at: at + area(ij)] = compute_tile(pcs, pcs, rows, cols).reshape(-1)
         at += area(ij)
-    gathered = [torch.empty_like(mine) for _ in range(world)]
-    dist_.all_gather(gathered, mine, group=group)
-    full = mine.new_empty((n, n))
-    for r in range(world):
-        at = 0
-        for ij in owner[r]:
-            (r0, r1), (c0, c1) = bounds[ij[0]], bounds[ij[1]]
-            tile = gathered[r][at: at + area(ij)].view(r1 - r0, c1 - c0)
-            full[r0:r1, c0:c1] = tile
-            if ij[0] != ij[1]:
-                full[c0:c1, r0:r1] = tile.t()
-            at += area(ij)
-    return full
+    gathered = mine.new_empty((world * longest,))
+    dist_.all_gather_into_tensor(gathered, mine, group=group)
+    full = mine.new_empty((n * n,))
+    full[dst] = gathered[src]
+    full[mdst] = gathered[msrc]
+    return full.view(n, n)
 
 
 def _same_set(a, b):
     return a.shape == b.shape and a.data_ptr() == b.data_ptr() and a.stride() == b.stride()
+
+
+def _device_of(t):
+    return t.device if t.is_cuda else torch.device("cuda", torch.cuda.current_device())
 
 
 def pairwise_emd(sample_pcs, ref_pcs, group=None):
@@ -114,20 +146,37 @@ def pairwise_emd(sample_pcs, ref_pcs, group=None):
 
 def pairwise_cd(sample_pcs, ref_pcs, group=None, compute_tile=None):
     """Full [N_sample, N_ref] Chamfer matrix on every rank.  `compute_tile(sample, ref, rows, cols)` defaults to
-    the CUDA kernel; tests substitute a CPU function to exercise the tiling + collective with gloo."""
+    the CUDA kernel; tests substitute a CPU function to exercise the tiling + collective with gloo.
+
+    HOST inputs (the end-to-end path: compute_all_metrics is handed CPU tensors by a loader) are not replicated: each
+    rank copies only the rows and columns of its own tile to its GPU (750 of 2000 clouds at 8 ranks)."""
     world = dist_.get_world_size(group)
     rank = dist_.get_rank(group)
     n_rows, n_cols = sample_pcs.shape[0], ref_pcs.shape[0]
-    if compute_tile is None:
+    host = compute_tile is None and not sample_pcs.is_cuda
+    kernel = ops.cd_allpairs if compute_tile is None else compute_tile
+    on_gpu = compute_tile is None or compute_tile is ops.emd_allpairs
+    if compute_tile is None and _same_set(sample_pcs, ref_pcs) and n_rows >= 128:
         # rr / ss matrices: every unordered pair once (CD is symmetric); below ~128 clouds the extra launches cost more
-        if _same_set(sample_pcs, ref_pcs) and n_rows >= 128:
-            return pairwise_cd_symmetric(sample_pcs, group=group)
-        compute_tile = ops.cd_allpairs
+        dev_set = sample_pcs.to(_device_of(sample_pcs), non_blocking=True) if host else sample_pcs
+        return pairwise_cd_symmetric(dev_set, group=group)
     rows, cols = tile_of(rank, world, n_rows, n_cols)
     mr, mc = max_tile(world, n_rows, n_cols)
-    mine = sample_pcs.new_zeros((mr, mc))
-    if rows[1] > rows[0] and cols[1] > cols[0]:
-        mine[: rows[1] - rows[0], : cols[1] - cols[0]] = compute_tile(sample_pcs, ref_pcs, rows, cols)
-    gathered = [torch.empty_like(mine) for _ in range(world)]
-    dist_.all_gather(gathered, mine, group=group)
-    return assemble(gathered, world, n_rows, n_cols, mine)
+    nr, nc = rows[1] - rows[0], cols[1] - cols[0]
+    if on_gpu and not sample_pcs.is_cuda:
+        dev = _device_of(sample_pcs)
+        a = sample_pcs[rows[0]:rows[1]].to(dev, non_blocking=True)
+        b = ref_pcs[cols[0]:cols[1]].to(dev, non_blocking=True)
+        mine = a.new_zeros((mr, mc))
+        if nr > 0 and nc > 0:
+            kernel(a, b, (0, nr), (0, nc), out=mine[:nr, :nc])
+    else:
+        mine = sample_pcs.new_zeros((mr, mc))
+        if nr > 0 and nc > 0:
+            if on_gpu:
+                kernel(sample_pcs, ref_pcs, rows, cols, out=mine[:nr, :nc])     # written in place, row stride mc
+            else:
+                mine[:nr, :nc] = kernel(sample_pcs, ref_pcs, rows, cols)
+    gathered = mine.new_empty((world * mr, mc))                 # ranks concatenated along dim 0 (the layout gloo accepts too)
+    dist_.all_gather_into_tensor(gathered, mine, group=group)
+    return assemble(gathered.view(world, mr, mc), world, n_rows, n_cols)

@@ -79,13 +79,21 @@ def EMD_CD(sample_pcs, ref_pcs, batch_size, accelerated_cd=False, reduced=True):
 
 
 def _pairwise_EMD_CD_(sample_pcs, ref_pcs, batch_size=None, accelerated_cd=True):
-    """evaluation_metrics.py:85-121.  Returns (all_cd, all_emd), both [N_sample, N_ref] (all_emd None if skipped)."""
+    """evaluation_metrics.py:85-121.  Returns (all_cd, all_emd), both [N_sample, N_ref] (all_emd None if skipped).
+    CUDA inputs as in the reference's call (PDGNet_v2.py:319); HOST inputs are also accepted (the end-to-end path): the
+    copies to the current CUDA device then happen here -- under torch.distributed only this rank's rows / columns -- and the
+    matrices come back on that device."""
     from . import dist
     sample_pcs = sample_pcs.contiguous().float()
-    ref_pcs = ref_pcs.contiguous().float()
+    ref_pcs = ref_pcs.contiguous().float() if ref_pcs is not sample_pcs else sample_pcs
     skip = _skip_emd()
     if not skip:
         _check_emd_size(sample_pcs.size(1), ref_pcs.size(1))
+    if not sample_pcs.is_cuda and (not skip or not dist.is_distributed()):
+        dev = torch.device("cuda", torch.cuda.current_device())
+        same = ref_pcs is sample_pcs
+        sample_pcs = sample_pcs.to(dev, non_blocking=True)
+        ref_pcs = sample_pcs if same else ref_pcs.to(dev, non_blocking=True)
     if dist.is_distributed():
         return dist.pairwise_cd(sample_pcs, ref_pcs), (None if skip else dist.pairwise_emd(sample_pcs, ref_pcs))
     return ops.cd_allpairs(sample_pcs, ref_pcs), (None if skip else ops.emd_allpairs(sample_pcs, ref_pcs))

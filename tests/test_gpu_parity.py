@@ -680,3 +680,43 @@ def test_local_stats_against_numpy(dev):
     cov_ref = np.einsum("bjsa,bjsc->bjac", t, t) / 20.0
     np.testing.assert_allclose(C(mu), mu_ref, rtol=1e-6, atol=1e-7)
     np.testing.assert_allclose(C(cov).reshape(2, 90, 3, 3), cov_ref, rtol=1e-5, atol=1e-7)
+
+
+# ------------------------------------------------------------------------------------------------ debugging aids
+def test_verify_mode_catches_out_of_range_indices(dev):
+    """PDGN_B200_VERIFY=1 (read once per process, hence the subprocess): a gather with an index outside [0, n) returns
+    PDGN_ERR_INDEX instead of reading out of bounds; valid calls are unaffected and equal the unverified result."""
+    import os
+    import subprocess
+    import sys
+    code = r"""
+import sys, torch
+sys.path.insert(0, %r)
+from pdgn_b200 import ops
+from pdgn_b200._lib import PdgnError
+feat = torch.randn(2, 16, 64, device='cuda')
+idx = torch.randint(0, 64, (2, 32, 8), device='cuda', dtype=torch.int32)
+good = ops.group_fwd(feat, idx)
+assert torch.equal(good, torch.gather(feat.unsqueeze(2).expand(-1, -1, 32, -1), 3, idx.long().unsqueeze(1).expand(-1, 16, -1, -1)))
+ops.group_bwd(torch.randn_like(good), idx, 64)
+bad = idx.clone(); bad[1, 5, 3] = 64
+for call in (lambda: ops.group_fwd(feat, bad), lambda: ops.group_bwd(torch.randn_like(good), bad, 64),
+             lambda: ops.edge_feat_fwd(feat, bad.long()), lambda: ops.local_stats_fwd(torch.randn(2, 64, 3, device='cuda'), bad)):
+    try:
+        call()
+    except PdgnError as e:
+        assert 'index out of range' in str(e), str(e)
+    else:
+        raise SystemExit('out-of-range index not caught')
+neg = idx.clone(); neg[0, 0, 0] = -1
+try:
+    ops.interp_fwd(feat, neg[:, :, :3].contiguous(), torch.rand(2, 32, 3, device='cuda'))
+except PdgnError as e:
+    assert 'index out of range' in str(e)
+else:
+    raise SystemExit('negative index not caught')
+print('verify ok')
+""" % os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    env = dict(os.environ, PDGN_B200_VERIFY="1")
+    r = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, timeout=600, env=env)
+    assert r.returncode == 0 and "verify ok" in r.stdout, r.stdout + r.stderr
