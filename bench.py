@@ -371,7 +371,7 @@ def main():
             line["reference_gpu"] = _guard(bench_reference_gpu, dev, value)
             n_s, n_r = 24, 50  # ~10 s of host work: a bounded sample of the 1000 x 1000 workload
             rate, dt = cpu_reference_rate(n_s, n_r)
-            line["cpu_baseline"] = {"value": rate, "unit": UNIT, "cores": os.cpu_count() or 1, "kind": "port", "seconds": dt,
+            line["cpu_baseline"] = {"value": rate, "unit": UNIT, "cores": os.cpu_count() or 1, "kind": _CPU_KIND or "port", "seconds": dt,
                                     "sample": "%d x %d cloud pairs of 2048 points (reference Gram-form distChamfer loop, batch_size 50)" % (n_s, n_r)}
     # sanity: the e2e result equals the device-resident one
     line["e2e"]["matches_device_result"] = bool(torch.equal(out.cpu(), out_e2e))
