@@ -498,8 +498,23 @@ static bool select_plan(int n, int k, int G, int* log2ss, int* gsz) {
     return false;
 }
 
+// knn_gram.cu: the full-size-cloud kernel (register-blocked Gram-form filter + lane-private exact selection)
+bool knn_gram_eligible(int n, int k);
+int knn_gram_launch(const float* xyz, const float* new_xyz, int b, int n, int m, int k, int* idx, float* dist2, cudaStream_t st);
+
 static int knn_dispatch(const float* xyz, const float* new_xyz, int b, int n, int m, int k, int* idx, float* dist2, cudaStream_t st) {
     int log2ss = 0, gsz = 0;
+    // Full-size clouds with enough queries to give every SM a 512-query CTA: the round-2 kernel.  Fewer queries (the training
+    // shapes) keep the sliced select kernel below, whose CTAs shrink until the grid covers the chip.
+    {
+        static const char* impl = tune_env("PDGN_KNN_IMPL");   // tuning hook: "gram" / "select" force one kernel family
+        // One 512-query CTA per SM and ~85 us per CTA whatever the query count: worth it when the last wave is >= 70 % full
+        // (measured cross-over against the select kernel: ~100 CTAs; profiles/r02_knn_gram_vs_select.txt)
+        const long long ctas = (long long)b * ((m + 511) / 512);
+        const long long waves = (ctas + 147) / 148;
+        const bool want = impl ? impl[0] == 'g' : (ctas * 10 >= waves * 148 * 7);
+        if (want && knn_gram_eligible(n, k)) return knn_gram_launch(xyz, new_xyz, b, n, m, k, idx, dist2, st);
+    }
     // tiny k with few candidates: register-resident lists (every lane inserts ~k ln(n) times, which keeps the whole warp in
     // the divergent insertion path once n is in the hundreds: 22 instr/pair at n = 1024, so larger n goes to the select kernel)
     static const bool force_smallk = tune_env("PDGN_KNN_SMALLK") != nullptr;  // tuning hook

@@ -720,3 +720,62 @@ print('verify ok')
     env = dict(os.environ, PDGN_B200_VERIFY="1")
     r = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, timeout=600, env=env)
     assert r.returncode == 0 and "verify ok" in r.stdout, r.stdout + r.stderr
+
+
+def test_knn_gram_kernel_forced_over_parity_shapes(dev):
+    """csrc/knn_gram.cu (the full-size-cloud kNN kernel: Gram-form filter + lane-private exact selection) is chosen by the
+    dispatcher only when the query count fills the chip; here it is FORCED (PDGN_B200_TUNE=1 PDGN_KNN_IMPL=gram, read once per
+    process, hence the subprocess) over every shape it is eligible for -- ragged n / m, the three subgroup sizes, ties,
+    duplicates (survivor overflow -> cooperative exact path), index-coherent clouds, clouds far from the origin (error margin
+    of the Gram filter), NaN / inf / huge coordinates -- and must equal the oracle bit for bit, indices and distances."""
+    import os
+    import subprocess
+    import sys
+    code = r"""
+import sys
+import numpy as np, torch
+sys.path.insert(0, %r); sys.path.insert(0, %r)
+from conftest import clouds_sphere, clouds_ties, clouds_uniform
+from oracle import cpu as ocpu
+from pdgn_b200 import ops
+dev = torch.device('cuda:0')
+def coherent(rng, b, n, _3):
+    v = clouds_sphere(rng, b, n, 3)
+    for i in range(b):
+        key = np.floor((v[i] + 1.2) * 4).astype(np.int64)
+        v[i] = v[i][np.lexsort((v[i][:, 2], key[:, 2], key[:, 1], key[:, 0]))]
+    return v
+def dup_heavy(rng, b, n, _3):
+    v = clouds_uniform(rng, b, n, 3)
+    v[:, n // 2:] = v[:, : n - n // 2]
+    v[:, : n // 8] = v[:, :1]
+    return v
+def far(rng, b, n, _3):
+    return (clouds_uniform(rng, b, n, 3) * 0.5 + np.array([40.0, -25.0, 10.0], np.float32)).astype(np.float32)
+cases = [(clouds_uniform, 2, 300, None, 20), (clouds_sphere, 3, 1000, 257, 20), (clouds_ties, 2, 512, None, 20), (clouds_sphere, 2, 2048, None, 20),
+         (clouds_ties, 2, 2048, 600, 20), (clouds_uniform, 2, 2048, 300, 12), (clouds_uniform, 2, 501, 130, 20), (clouds_uniform, 2, 1001, 130, 20),
+         (clouds_uniform, 2, 2039, 130, 16), (clouds_sphere, 2, 2048, 2048, 1), (clouds_uniform, 2, 1024, 2048, 3), (coherent, 2, 2048, None, 20),
+         (coherent, 2, 1024, 700, 20), (dup_heavy, 2, 2048, 515, 20), (far, 2, 2048, 300, 20), (clouds_uniform, 1, 1500, 513, 20),
+         (clouds_uniform, 2, 257, 257, 20), (clouds_sphere, 35, 2048, None, 20)]
+for ci, (maker, b, n, m, k) in enumerate(cases):
+    rng = np.random.default_rng(100 + ci)
+    xyz = maker(rng, b, n, 3)
+    q = xyz if m is None else maker(rng, b, m, 3)
+    idx, d2 = ops.knn_xyz(k, torch.from_numpy(xyz).to(dev), torch.from_numpy(q).to(dev), return_dist=True)
+    oi, od = ocpu.knn_xyz(xyz, q, k)
+    assert np.array_equal(idx.cpu().numpy(), oi), (ci, 'idx')
+    assert np.array_equal(d2.cpu().numpy(), od), (ci, 'dist2')
+rng = np.random.default_rng(5)
+xyz, q = clouds_uniform(rng, 1, 600, 3), clouds_uniform(rng, 1, 40, 3)
+xyz[0, 7] = np.nan; xyz[0, 100, 1] = np.inf; xyz[0, 200] = 1e30; q[0, 3, 0] = np.nan; q[0, 5] = np.inf; q[0, 9] = 3e19
+idx, d2 = ops.knn_xyz(20, torch.from_numpy(xyz).to(dev), torch.from_numpy(q).to(dev), return_dist=True)
+oi, od = ocpu.knn_xyz(xyz, q, 20)
+assert np.array_equal(idx.cpu().numpy(), oi) and np.array_equal(d2.cpu().numpy(), od)
+# idx-only call (dist2 = NULL), as pointops.knnquery makes it
+xyz = clouds_sphere(rng, 2, 2048, 3)
+assert np.array_equal(ops.knn_xyz(20, torch.from_numpy(xyz).to(dev)).cpu().numpy(), ocpu.knn_xyz(xyz, xyz, 20)[0])
+print('gram ok')
+""" % (os.path.dirname(os.path.dirname(os.path.abspath(__file__))), os.path.dirname(os.path.abspath(__file__)))
+    env = dict(os.environ, PDGN_B200_TUNE="1", PDGN_KNN_IMPL="gram")
+    r = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, timeout=900, env=env)
+    assert r.returncode == 0 and "gram ok" in r.stdout, r.stdout[-2000:] + r.stderr[-4000:]
