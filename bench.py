@@ -599,7 +599,17 @@ def bench_cfg3(dev):
             total.backward()
         return total
 
-    res = {"batch": B, "loss_side_fwd_ms": _ev_ms(lambda: loss_side(False)), "loss_side_fwd_bwd_ms": _ev_ms(lambda: loss_side(True))}
+    def loss_side_batched(backward):
+        leaves = [pts[n].clone().requires_grad_(backward) for n in (256, 512, 1024, 2048)]
+        total = local_pair.shape_losses(leaves, 20).sum()
+        if backward:
+            total.backward()
+        return total
+
+    res = {"batch": B, "loss_side_fwd_ms": _ev_ms(lambda: loss_side_batched(False)), "loss_side_fwd_bwd_ms": _ev_ms(lambda: loss_side_batched(True)),
+           "loss_side_launches": {"fwd": 6, "bwd": 5, "note": "pdgn_shape_loss_fwd/bwd: all 9 kNN / 9 statistics / 24 minimum problems of the "
+                                  "step per operator launch; what the drop-in runs for the trainer's six get_local_pair calls"},
+           "loss_side_per_call_fwd_ms": _ev_ms(lambda: loss_side(False)), "loss_side_per_call_fwd_bwd_ms": _ev_ms(lambda: loss_side(True))}
     stages = {}
     for c, n in [(32, 128), (64, 256), (128, 512), (256, 1024)]:
         x = torch.randn(B, c, n, device=dev)

@@ -159,6 +159,20 @@ int pdgn_local_pair_fwd(const float *pt1, const float *pt2, int b, int m, int n,
 int pdgn_local_pair_bwd(int b, int m, int n, int k, const float *grad_out, float *grad_pt1, float *grad_pt2,
                         void *workspace, size_t workspace_bytes, void *stream);
 
+/* ---- the shape-preserving loss of one generator step, every operator in ONE launch ---------------------------------
+ * Replaces the six get_local_pair calls of PDGNet_v2.train (models/PDGNet_v2.py:232-237) on the generator's `levels` outputs
+ * pts[l] [b,3,npts[l]] (device pointers, l = 0..levels-1, 2 <= levels <= 4): for every level pair (a < c), in the reference's
+ * order (0,1) (0,2) (0,3) (1,2) (1,3) (2,3), out[2p] = like_mu and out[2p+1] = like_var of get_local_pair(pts[a], pts[c]).
+ * The 9 kNN, 9 statistics and 24 directional-minimum problems run from problem-descriptor tables: 6 launches forward, 4 +
+ * one memset backward.  Same conventions as pdgn_local_pair_*: the workspace (pdgn_shape_loss_workspace bytes, 16-byte
+ * aligned) carries indices / statistics / arg-minima to the backward call; grad_pts[l] [b,3,npts[l]] are ADDED into (a
+ * NULL entry skips that level); grad_out[2 * pairs] (device) holds the upstream gradients.  1 <= k <= 64. */
+size_t pdgn_shape_loss_workspace(int b, int levels, const int *npts, int k);
+int pdgn_shape_loss_fwd(const float *const *pts, int b, int levels, const int *npts, int k, float *out, void *workspace,
+                        size_t workspace_bytes, void *stream);
+int pdgn_shape_loss_bwd(int b, int levels, const int *npts, int k, const float *grad_out, float *const *grad_pts,
+                        void *workspace, size_t workspace_bytes, void *stream);
+
 /* ---- feature-space kNN of the generator ---------------------------------------------------------------
  * Replaces bmm + torch.sort + slice in get_edge_features{,_xyz} (models/PDGNet_v2.py:449-459, :492-502).
  * x [b,c,n] -> idx int64 [b,n,k]: ranks skip..skip+k-1 of the ascending (d2, index) order of exact FP32

@@ -43,6 +43,9 @@ SIGNATURES = {
     "pdgn_local_pair_workspace": (_SZ, [_I, _I, _I, _I]),
     "pdgn_local_pair_fwd": (_I, [_P, _P, _I, _I, _I, _I, _P, _P, _SZ, _P]),
     "pdgn_local_pair_bwd": (_I, [_I, _I, _I, _I, _P, _P, _P, _P, _SZ, _P]),
+    "pdgn_shape_loss_workspace": (_SZ, [_I, _I, _P, _I]),
+    "pdgn_shape_loss_fwd": (_I, [_P, _I, _I, _P, _I, _P, _P, _SZ, _P]),
+    "pdgn_shape_loss_bwd": (_I, [_I, _I, _P, _I, _P, _P, _P, _SZ, _P]),
     "pdgn_knn_feat": (_I, [_P, _I, _I, _I, _I, _I, _P, _P, _P]),
     "pdgn_edge_feat_fwd": (_I, [_P, _P, _I, _I, _I, _I, _P, _P]),
     "pdgn_edge_feat_bwd": (_I, [_P, _P, _I, _I, _I, _I, _P, _P]),

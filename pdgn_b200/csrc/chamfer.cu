@@ -11,6 +11,7 @@
 // Layout: a CTA owns CH_Q*128 query points of one batch element (CH_Q per thread, in registers) and streams the
 // candidate set through shared memory as SoA planes (warp-broadcast LDS.128 = 4 candidates per plane per load).
 #include "common.cuh"
+#include "multi.cuh"
 
 namespace pdgn {
 
@@ -39,15 +40,14 @@ __device__ __forceinline__ float sqdist(const float (&q)[D], const float (&p)[D]
 // minima, exactly what a single in-order scan gives).  The training shapes have only a few hundred queries per batch
 // element: with S = 1 they put one warp on each scheduler (27 us for 35 x 1024 x 1024, 21 % of the issue roofline).
 template <int D, int S>
-__global__ void __launch_bounds__(CH_T * S) nn_min_kernel(const float* __restrict__ x, const float* __restrict__ y, int nx, int ny,
-                                                         float* __restrict__ mind, int* __restrict__ argm) {
+__device__ __forceinline__ void nn_min_body(const float* __restrict__ x, const float* __restrict__ y, int nx, int ny,
+                                            float* __restrict__ mind, int* __restrict__ argm, int bx, int bz) {
     constexpr int CH_TILE = ChTile<D>::value;
     constexpr int MERGE = S > 1 ? 2 * S * CH_T * CH_Q : 0;          // floats needed to merge the slices
     constexpr int SMEM = D * CH_TILE > MERGE ? D * CH_TILE : MERGE;
     __shared__ __align__(16) float tile[SMEM];
-    const int bz = blockIdx.y;
     const int qt = threadIdx.x % CH_T, slice = threadIdx.x / CH_T;  // slice is warp-uniform (CH_T is a multiple of 32)
-    const int q0 = (blockIdx.x * CH_T + qt) * CH_Q;
+    const int q0 = (bx * CH_T + qt) * CH_Q;
     float q[CH_Q][D];
     float best[CH_Q];
     int besti[CH_Q];
@@ -124,6 +124,38 @@ __global__ void __launch_bounds__(CH_T * S) nn_min_kernel(const float* __restric
         }
 }
 
+template <int D, int S>
+__global__ void __launch_bounds__(CH_T * S) nn_min_kernel(const float* __restrict__ x, const float* __restrict__ y, int nx, int ny,
+                                                         float* __restrict__ mind, int* __restrict__ argm) {
+    nn_min_body<D, S>(x, y, nx, ny, mind, argm, blockIdx.x, blockIdx.y);
+}
+
+// problem-descriptor launches (multi.cuh)
+template <int D, int S>
+__global__ void __launch_bounds__(CH_T * S) nn_min_multi_kernel(const __grid_constant__ MinTable tb) {
+    const MinProb& pr = tb.p[multi_find(tb, blockIdx.x)];
+    nn_min_body<D, S>(pr.x, pr.y, pr.nx, pr.ny, pr.mind, pr.argm, blockIdx.x - pr.cta0, blockIdx.y);
+}
+
+// backward of sum_i g * inv_m * min_i for every problem of the table: d/dx_i = 2 g inv_m (x_i - y_a(i)), opposite sign on y_a(i)
+__global__ void __launch_bounds__(256) chamfer_bwd_multi_kernel(const __grid_constant__ MinTable tb, int d) {
+    const MinProb& pr = tb.p[multi_find(tb, blockIdx.x)];
+    const int bz = blockIdx.y;
+    const int i = (blockIdx.x - pr.cta0) * 256 + threadIdx.x;
+    if (i >= pr.nx) return;
+    const int j = pr.argm[(size_t)bz * pr.nx + i];
+    const float g = 2.f * __ldg(pr.gscale) * pr.inv_m;
+    const float* xp = pr.x + ((size_t)bz * pr.nx + i) * d;
+    const float* yp = pr.y + ((size_t)bz * pr.ny + j) * d;
+    float* gx = pr.gx + ((size_t)bz * pr.nx + i) * d;
+    float* gy = pr.gy + ((size_t)bz * pr.ny + j) * d;
+    for (int c = 0; c < d; ++c) {
+        const float v = g * (xp[c] - yp[c]);
+        atomicAdd(gx + c, v);
+        atomicAdd(gy + c, -v);
+    }
+}
+
 // d/dx_i of w_i * |x_i - y_a(i)|^2 = 2 w_i (x_i - y_a(i)), and the opposite sign on y_a(i) (nndistance.cu:129-148).
 __global__ void __launch_bounds__(256) chamfer_bwd_kernel(const float* __restrict__ x, const float* __restrict__ y, int nx, int ny,
                                                          int d, const float* __restrict__ w, const int* __restrict__ arg,
@@ -177,6 +209,36 @@ static int dispatch_nn_min(const float* x, const float* y, int b, int nx, int ny
 #undef PDGN_CASE
     }
     return PDGN_ERR_UNSUPPORTED;
+}
+
+template <int D>
+static int nn_min_multi_launch_d(MinTable& tb, int b, cudaStream_t st) {
+    constexpr int S = D <= 8 ? 4 : 2;       // slices per CTA: the training shapes have few queries per batch element
+    int ctas = 0;
+    for (int i = 0; i < tb.count; ++i) {
+        tb.p[i].cta0 = ctas;
+        ctas += (tb.p[i].nx + CH_T * CH_Q - 1) / (CH_T * CH_Q);
+    }
+    nn_min_multi_kernel<D, S><<<dim3(ctas, b), CH_T * S, 0, st>>>(tb);
+    PDGN_CHECK_LAUNCH();
+    return PDGN_OK;
+}
+int nn_min_multi_launch(MinTable& tb, int b, int d, cudaStream_t st) {
+    if (tb.count < 1 || tb.count > MULTI_MAX) return PDGN_ERR_UNSUPPORTED;
+    if (d == 3) return nn_min_multi_launch_d<3>(tb, b, st);
+    if (d == 9) return nn_min_multi_launch_d<9>(tb, b, st);
+    return PDGN_ERR_UNSUPPORTED;
+}
+int chamfer_bwd_multi_launch(MinTable& tb, int b, int d, cudaStream_t st) {
+    if (tb.count < 1 || tb.count > MULTI_MAX) return PDGN_ERR_UNSUPPORTED;
+    int ctas = 0;
+    for (int i = 0; i < tb.count; ++i) {
+        tb.p[i].cta0 = ctas;
+        ctas += (tb.p[i].nx + 255) / 256;
+    }
+    chamfer_bwd_multi_kernel<<<dim3(ctas, b), 256, 0, st>>>(tb, d);
+    PDGN_CHECK_LAUNCH();
+    return PDGN_OK;
 }
 
 }  // namespace pdgn

@@ -25,6 +25,7 @@
 // Generic path (knn_generic_kernel): any k <= 128, any n; threshold-guarded insertion into a shared-memory list.
 #include <cstdlib>
 #include "common.cuh"
+#include "multi.cuh"
 
 namespace pdgn {
 
@@ -234,14 +235,13 @@ struct alignas(16) KsWarp {
 // each selects 32/S of the queries.  Used when the batch has too few queries to fill the chip with one warp per block (the
 // training shapes: 256..1024 queries per cloud); needs the single resident tile (n <= KS_TILE) and subgroups of <= 16.
 template <int G, int NWARPS, int S>
-__global__ void __launch_bounds__(NWARPS * 32) knn_select_kernel(const float* __restrict__ xyz, const float* __restrict__ new_xyz,
-                                                                int n, int m, int k, int log2ss, int gsz, int* __restrict__ idx,
-                                                                float* __restrict__ dist2) {
+__device__ __forceinline__ void knn_select_body(const float* __restrict__ xyz, const float* __restrict__ new_xyz, int n, int m, int k,
+                                                int log2ss, int gsz, int* __restrict__ idx, float* __restrict__ dist2, int bx, int bz) {
     constexpr int THREADS = NWARPS * 32;
     constexpr int NQ = NWARPS / S;  // query blocks per CTA
     extern __shared__ __align__(16) unsigned char smem_raw[];
     float* tile = reinterpret_cast<float*>(smem_raw);  // [3][KS_TILE]
-    const int bz = blockIdx.y, t = threadIdx.x, lane = t & 31, warp = t >> 5;
+    const int t = threadIdx.x, lane = t & 31, warp = t >> 5;
     const int qblock = warp / S, slice = warp % S;
     KsWarp<G, S>* wsm = reinterpret_cast<KsWarp<G, S>*>(tile + 3 * KS_TILE) + qblock;
     KsSelect& sel = wsm->sel[slice];
@@ -250,7 +250,7 @@ __global__ void __launch_bounds__(NWARPS * 32) knn_select_kernel(const float* __
     const int nsub = (n + ss - 1) >> log2ss;          // <= KS_NSUB
     const int ng = (nsub + gsz - 1) / gsz;            // <= G
     const float* pb = xyz + (size_t)bz * n * 3;
-    const int q0 = (blockIdx.x * NQ + qblock) * 32;   // first query of this block
+    const int q0 = (bx * NQ + qblock) * 32;   // first query of this block
     const int qmine = max(0, min(q0 + lane, m - 1));
     const float* qp = new_xyz + ((size_t)bz * m + qmine) * 3;
     const float qx = qp[0], qy = qp[1], qz = qp[2];
@@ -468,6 +468,21 @@ __global__ void __launch_bounds__(NWARPS * 32) knn_select_kernel(const float* __
     }
 }
 
+template <int G, int NWARPS, int S>
+__global__ void __launch_bounds__(NWARPS * 32) knn_select_kernel(const float* __restrict__ xyz, const float* __restrict__ new_xyz,
+                                                                int n, int m, int k, int log2ss, int gsz, int* __restrict__ idx,
+                                                                float* __restrict__ dist2) {
+    knn_select_body<G, NWARPS, S>(xyz, new_xyz, n, m, k, log2ss, gsz, idx, dist2, blockIdx.x, blockIdx.y);
+}
+
+// problem-descriptor launch (multi.cuh): CTA -> (problem, query block)
+template <int G, int NWARPS, int S>
+__global__ void __launch_bounds__(NWARPS * 32) knn_select_multi_kernel(const __grid_constant__ KnnTable tb, int k) {
+    const int pi = multi_find(tb, blockIdx.x);
+    const KnnProb& pr = tb.p[pi];
+    knn_select_body<G, NWARPS, S>(pr.xyz, pr.q, pr.n, pr.m, k, pr.log2ss, pr.gsz, pr.idx, nullptr, blockIdx.x - pr.cta0, blockIdx.y);
+}
+
 template <int G, int NWARPS, int S = 1>
 static int launch_select(const float* xyz, const float* new_xyz, int b, int n, int m, int k, int log2ss, int gsz, int* idx,
                          float* dist2, cudaStream_t st) {
@@ -559,6 +574,26 @@ static int knn_dispatch(const float* xyz, const float* new_xyz, int b, int n, in
     PDGN_CUDA(cudaFuncSetAttribute(knn_generic_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     dim3 grid((m + KG_T - 1) / KG_T, b);
     knn_generic_kernel<<<grid, KG_T, smem, st>>>(xyz, new_xyz, n, m, k, idx, dist2);
+    PDGN_CHECK_LAUNCH();
+    return PDGN_OK;
+}
+
+int knn_multi_launch(KnnTable& tb, int b, int k, cudaStream_t st) {
+    // one instantiation for every problem: 64 groups, 16 warps = 4 query blocks x 4 candidate slices (the sliced form keeps
+    // the small query sets of the training shapes spread over many warps)
+    constexpr int G = 64, NWARPS = 16, S = 4, NQ = NWARPS / S;
+    if (k < 1 || k > 24 || tb.count < 1 || tb.count > 12) return PDGN_ERR_UNSUPPORTED;
+    int ctas = 0;
+    for (int i = 0; i < tb.count; ++i) {
+        KnnProb& pr = tb.p[i];
+        if (pr.n < 256 || pr.n > KS_TILE || pr.m < 1) return PDGN_ERR_UNSUPPORTED;
+        if (!select_plan(pr.n, k, G, &pr.log2ss, &pr.gsz) || pr.log2ss > 4) return PDGN_ERR_UNSUPPORTED;
+        pr.cta0 = ctas;
+        ctas += (pr.m + NQ * 32 - 1) / (NQ * 32);
+    }
+    const size_t smem = (size_t)3 * KS_TILE * 4 + (size_t)NQ * sizeof(KsWarp<G, S>);
+    PDGN_CUDA(cudaFuncSetAttribute(knn_select_multi_kernel<G, NWARPS, S>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    knn_select_multi_kernel<G, NWARPS, S><<<dim3(ctas, b), NWARPS * 32, smem, st>>>(tb, k);
     PDGN_CHECK_LAUNCH();
     return PDGN_OK;
 }

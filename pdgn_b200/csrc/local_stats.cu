@@ -10,16 +10,16 @@
 //   cov_ab  = (1/k) sum_s (x[idx_s][a] - mu_a)(x[idx_s][b] - mu_b)
 //   dL/dx[idx_s][c] += gmu_c / k + (1/k) sum_b (gcov_cb + gcov_bc) (x[idx_s][b] - mu_b)      (sum_s (x_s - mu) = 0)
 #include "common.cuh"
+#include "multi.cuh"
 
 namespace pdgn {
 
 constexpr int LS_T = 128;
 constexpr int LS_KMAX = 64;
 
-__global__ void __launch_bounds__(LS_T) local_stats_fwd_kernel(const float* __restrict__ xyz, const int* __restrict__ idx, int n, int m,
-                                                              int k, float* __restrict__ mu, float* __restrict__ cov) {
-    const int bz = blockIdx.y;
-    const int j = blockIdx.x * LS_T + threadIdx.x;
+__device__ __forceinline__ void local_stats_fwd_body(const float* __restrict__ xyz, const int* __restrict__ idx, int n, int m, int k,
+                                                     float* __restrict__ mu, float* __restrict__ cov, int bx, int bz) {
+    const int j = bx * LS_T + threadIdx.x;
     if (j >= m) return;
     const float* pb = xyz + (size_t)bz * n * 3;
     const int* ip = idx + ((size_t)bz * m + j) * k;
@@ -45,12 +45,16 @@ __global__ void __launch_bounds__(LS_T) local_stats_fwd_kernel(const float* __re
     co[6] = cxz * inv; co[7] = cyz * inv; co[8] = czz * inv;
 }
 
-__global__ void __launch_bounds__(LS_T) local_stats_bwd_kernel(const float* __restrict__ xyz, const int* __restrict__ idx,
-                                                              const float* __restrict__ mu, const float* __restrict__ gmu,
-                                                              const float* __restrict__ gcov, int n, int m, int k,
-                                                              float* __restrict__ gxyz) {
-    const int bz = blockIdx.y;
-    const int j = blockIdx.x * LS_T + threadIdx.x;
+__global__ void __launch_bounds__(LS_T) local_stats_fwd_kernel(const float* __restrict__ xyz, const int* __restrict__ idx, int n, int m,
+                                                              int k, float* __restrict__ mu, float* __restrict__ cov) {
+    local_stats_fwd_body(xyz, idx, n, m, k, mu, cov, blockIdx.x, blockIdx.y);
+}
+
+__device__ __forceinline__ void local_stats_bwd_body(const float* __restrict__ xyz, const int* __restrict__ idx,
+                                                     const float* __restrict__ mu, const float* __restrict__ gmu,
+                                                     const float* __restrict__ gcov, int n, int m, int k, float* __restrict__ gxyz,
+                                                     int bx, int bz) {
+    const int j = bx * LS_T + threadIdx.x;
     if (j >= m) return;
     const float* pb = xyz + (size_t)bz * n * 3;
     float* gb = gxyz + (size_t)bz * n * 3;
@@ -71,6 +75,44 @@ __global__ void __launch_bounds__(LS_T) local_stats_bwd_kernel(const float* __re
         atomicAdd(gb + (size_t)pi * 3 + 1, gy0 + inv * (sxy * tx + syy * ty + syz * tz));
         atomicAdd(gb + (size_t)pi * 3 + 2, gz0 + inv * (sxz * tx + syz * ty + szz * tz));
     }
+}
+
+__global__ void __launch_bounds__(LS_T) local_stats_bwd_kernel(const float* __restrict__ xyz, const int* __restrict__ idx,
+                                                              const float* __restrict__ mu, const float* __restrict__ gmu,
+                                                              const float* __restrict__ gcov, int n, int m, int k,
+                                                              float* __restrict__ gxyz) {
+    local_stats_bwd_body(xyz, idx, mu, gmu, gcov, n, m, k, gxyz, blockIdx.x, blockIdx.y);
+}
+
+// problem-descriptor launches (multi.cuh)
+__global__ void __launch_bounds__(LS_T) local_stats_multi_fwd_kernel(const __grid_constant__ StatTable tb, int k) {
+    const StatProb& pr = tb.p[multi_find(tb, blockIdx.x)];
+    local_stats_fwd_body(pr.xyz, pr.idx, pr.n, pr.m, k, pr.mu, pr.cov, blockIdx.x - pr.cta0, blockIdx.y);
+}
+__global__ void __launch_bounds__(LS_T) local_stats_multi_bwd_kernel(const __grid_constant__ StatTable tb, int k) {
+    const StatProb& pr = tb.p[multi_find(tb, blockIdx.x)];
+    local_stats_bwd_body(pr.xyz, pr.idx, pr.mu, pr.gmu, pr.gcov, pr.n, pr.m, k, pr.gxyz, blockIdx.x - pr.cta0, blockIdx.y);
+}
+
+static int stat_table_ctas(StatTable& tb) {
+    int ctas = 0;
+    for (int i = 0; i < tb.count; ++i) {
+        tb.p[i].cta0 = ctas;
+        ctas += (tb.p[i].m + LS_T - 1) / LS_T;
+    }
+    return ctas;
+}
+int local_stats_multi_fwd(StatTable& tb, int b, int k, cudaStream_t st) {
+    if (k < 1 || k > LS_KMAX || tb.count < 1 || tb.count > 12) return PDGN_ERR_UNSUPPORTED;
+    local_stats_multi_fwd_kernel<<<dim3(stat_table_ctas(tb), b), LS_T, 0, st>>>(tb, k);
+    PDGN_CHECK_LAUNCH();
+    return PDGN_OK;
+}
+int local_stats_multi_bwd(StatTable& tb, int b, int k, cudaStream_t st) {
+    if (k < 1 || k > LS_KMAX || tb.count < 1 || tb.count > 12) return PDGN_ERR_UNSUPPORTED;
+    local_stats_multi_bwd_kernel<<<dim3(stat_table_ctas(tb), b), LS_T, 0, st>>>(tb, k);
+    PDGN_CHECK_LAUNCH();
+    return PDGN_OK;
 }
 
 }  // namespace pdgn

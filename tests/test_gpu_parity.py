@@ -779,3 +779,63 @@ print('gram ok')
     env = dict(os.environ, PDGN_B200_TUNE="1", PDGN_KNN_IMPL="gram")
     r = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, timeout=900, env=env)
     assert r.returncode == 0 and "gram ok" in r.stdout, r.stdout[-2000:] + r.stderr[-4000:]
+
+
+# ------------------------------------------------------------------------------------------------ batched shape loss
+@pytest.mark.parametrize("b,npts", [(35, (256, 512, 1024, 2048)), (3, (300, 512, 700)), (2, (64, 2048)), (2, (256, 100, 512, 33))])
+def test_shape_losses_batched_equals_six_get_local_pair_calls(dev, b, npts):
+    """pdgn_shape_loss_fwd/bwd (csrc/shape_loss.cu: every operator of the step in one descriptor-table launch) against the
+    per-call path pdgn_local_pair_fwd/bwd on the same level pairs, in the trainer's order (PDGNet_v2.py:232-237): same kernel
+    bodies, so values agree to the summation order of the final sums and gradients to the atomics' order.  Levels below 256
+    points exercise the per-problem kNN fallback."""
+    from pdgn_b200 import local_pair
+    rng = np.random.default_rng(sum(npts) + b)
+    base = [G(np.ascontiguousarray(0.5 * clouds_sphere(rng, b, n, 3).transpose(0, 2, 1)), dev) for n in npts]
+    xs = [p.clone().requires_grad_(True) for p in base]
+    ys = [p.clone().requires_grad_(True) for p in base]
+    out = local_pair.shape_losses(xs, 20)
+    pairs = [(i, j) for i in range(len(npts)) for j in range(i + 1, len(npts))]
+    assert tuple(out.shape) == (2 * len(pairs),)
+    ref = []
+    for i, j in pairs:
+        mu, var = local_pair.get_local_pair(ys[i], ys[j], 20)      # not noted generator outputs: the per-call path
+        ref += [mu, var]
+    ref = torch.stack(ref)
+    torch.testing.assert_close(out, ref, rtol=2e-6, atol=0)
+    w = torch.linspace(0.5, 2.0, out.numel(), device=dev)
+    (out * w).sum().backward()
+    (ref * w).sum().backward()
+    for x, y in zip(xs, ys):
+        torch.testing.assert_close(x.grad, y.grad, rtol=1e-4, atol=1e-7)
+    # a level that needs no gradient gets none, and partial use of the outputs back-propagates zeros for the rest
+    zs = [p.clone().requires_grad_(i != 0) for i, p in enumerate(base)]
+    out2 = local_pair.shape_losses(zs, 20)
+    out2[1].backward()
+    assert zs[0].grad is None and all(z.grad is not None for z in zs[1:])
+
+
+def test_get_local_pair_answers_from_the_noted_generator_outputs(dev):
+    """The drop-in notes the generator's outputs; the first get_local_pair call on two of them evaluates all pairs at once and
+    the others are answered from that result -- identical values / gradients to the per-call path, whatever the call order."""
+    from pdgn_b200 import local_pair
+    rng = np.random.default_rng(9)
+    base = [G(np.ascontiguousarray(0.5 * clouds_sphere(rng, 4, n, 3).transpose(0, 2, 1)), dev) for n in (256, 512, 1024, 2048)]
+    xs = [p.clone().requires_grad_(True) for p in base]
+    ys = [p.clone().requires_grad_(True) for p in base]
+    local_pair.note_generator_outputs(tuple(xs))
+    order = [(2, 3), (0, 1), (0, 3), (1, 2), (0, 2), (1, 3)]
+    tot_x = sum(a + 2.0 * b_ for a, b_ in (local_pair.get_local_pair(xs[i], xs[j]) for i, j in order))
+    assert local_pair._noted["result"] is not None                     # the batched evaluation was used
+    tot_y = sum(a + 2.0 * b_ for a, b_ in (local_pair.get_local_pair(ys[i], ys[j]) for i, j in order))
+    torch.testing.assert_close(tot_x, tot_y, rtol=1e-5, atol=0)
+    tot_x.backward()
+    tot_y.backward()
+    for x, y in zip(xs, ys):
+        torch.testing.assert_close(x.grad, y.grad, rtol=1e-4, atol=1e-7)
+    # an in-place change of an output invalidates the note; swapped arguments are not a trainer pair
+    with torch.no_grad():
+        xs[1].mul_(1.0)
+    assert local_pair._noted_pair(xs[0], xs[1], 20) is None
+    local_pair.note_generator_outputs(tuple(ys))
+    assert local_pair._noted_pair(ys[1], ys[0], 20) is None
+    local_pair.note_generator_outputs(())
