@@ -302,11 +302,13 @@ __global__ void __launch_bounds__(512) group_bwd_pull_kernel(const float* __rest
 // channel chunks of one batch element; the CC rows of a chunk arrive by TMA bulk copy (cp.async.bulk + mbarrier) into
 // one of two shared buffers while the 1024 threads pull the previous chunk, so HBM streams continuously and the
 // latency of the list walk hides under it.  MODE 0: rows = grad_out[b,ch,:].  MODE 1: rows = g1 = grad_ee[b,c+ch,:],
-// plus the central term sum_s (g0 - g1)[i,s] read in place.
+// plus the central term sum_s (g0 - g1)[i,s] read in place.  MODE 2 (interpolation backward): the lists hold entries
+// e = 3 j + t of idx[b, 3 rowlen], the contribution of an entry is fmul(rows[ch][e / 3], wgt[b][e]).
 template <int CC, int MODE>
 __global__ void __launch_bounds__(1024, 1) pull_stream_kernel(const float* __restrict__ src, const int* __restrict__ offs,
                                                           const int* __restrict__ pos, int c, int ntargets, int rowlen, int k,
-                                                          int chunks_per_cta, float* __restrict__ dst) {
+                                                          int chunks_per_cta, float* __restrict__ dst,
+                                                          const float* __restrict__ wgt) {
     constexpr int NR = MODE == 1 ? 2 * CC : CC;    // rows staged per chunk (MODE 1: CC g0 rows, then CC g1 rows)
     constexpr int ECACHE = 16;                     // list entries cached in registers across the chunks
     extern __shared__ __align__(128) float buf[];  // [2][NR*rowlen]
@@ -321,7 +323,12 @@ __global__ void __launch_bounds__(1024, 1) pull_stream_kernel(const float* __res
     const float* rows_b = MODE == 0 ? src + (size_t)bz * c * rowlen : g0_b + (size_t)c * rowlen;
     float* dst_b = dst + (size_t)bz * c * ntargets;
     const int* ob = offs + (size_t)bz * (ntargets + 1);
-    const int* pb = pos + (size_t)bz * rowlen;
+    const int* pb = pos + (size_t)bz * rowlen * (MODE == 2 ? 3 : 1);
+    const float* wb = MODE == 2 ? wgt + (size_t)bz * rowlen * 3 : nullptr;
+    // contribution of list entry e to channel ch of the staged chunk
+    auto contrib = [&](const float* rows, int ch, int e) {
+        return MODE == 2 ? __fmul_rn(rows[ch * rowlen + e / 3], __ldg(wb + e)) : rows[ch * rowlen + e];
+    };
     auto issue = [&](int i) {
         const int ch0 = (chunk0 + i) * CC;
         const unsigned bytes = (unsigned)min(CC, c - ch0) * (unsigned)rowlen * 4u;
@@ -346,12 +353,17 @@ __global__ void __launch_bounds__(1024, 1) pull_stream_kernel(const float* __res
     // list of target tid in registers, so the per-chunk work is shared-memory gathers only
     const bool single = ntargets <= 1024;
     int ca = 0, clen = 0, ec[ECACHE];
+    float wc[MODE == 2 ? ECACHE : 1];
     if (single && tid < ntargets) {
         ca = ob[tid];
         clen = ob[tid + 1] - ca;
     }
 #pragma unroll
-    for (int u = 0; u < ECACHE; ++u) ec[u] = (single && u < clen && clen <= ECACHE) ? __ldg(pb + ca + u) : 0;
+    for (int u = 0; u < ECACHE; ++u) {
+        const int e = (single && u < clen && clen <= ECACHE) ? __ldg(pb + ca + u) : 0;
+        ec[u] = MODE == 2 ? e / 3 : e;
+        if (MODE == 2) wc[u] = __ldg(wb + e);
+    }
 
     for (int i = 0; i < nloc; ++i) {
         const int ch0 = (chunk0 + i) * CC;
@@ -381,14 +393,15 @@ __global__ void __launch_bounds__(1024, 1) pull_stream_kernel(const float* __res
                 for (int u = 0; u < ECACHE; ++u)
                     if (u < len) {
 #pragma unroll
-                        for (int ch = 0; ch < CC; ++ch) acc[ch] += rows[ch * rowlen + ec[u]];
+                        for (int ch = 0; ch < CC; ++ch)
+                            acc[ch] += MODE == 2 ? __fmul_rn(rows[ch * rowlen + ec[u]], wc[u]) : rows[ch * rowlen + ec[u]];
                     }
             } else if (len > PULL_LONG) {
                 const int slot = atomicAdd(&nlong, 1);
                 if (slot < 512) longlist[slot] = p;  // the warp pass below adds the list sum after this thread's store
-                else pull_list<CC>(pb, a, a + len, acc, [&](int ch, int e) { return rows[ch * rowlen + e]; });
+                else pull_list<CC>(pb, a, a + len, acc, [&](int ch, int e) { return contrib(rows, ch, e); });
             } else {
-                pull_list<CC>(pb, a, a + len, acc, [&](int ch, int e) { return rows[ch * rowlen + e]; });
+                pull_list<CC>(pb, a, a + len, acc, [&](int ch, int e) { return contrib(rows, ch, e); });
             }
 #pragma unroll
             for (int ch = 0; ch < CC; ++ch)
@@ -401,7 +414,7 @@ __global__ void __launch_bounds__(1024, 1) pull_stream_kernel(const float* __res
             float acc[CC];
 #pragma unroll
             for (int ch = 0; ch < CC; ++ch) acc[ch] = 0.f;
-            pull_list_warp<CC>(pb, ob[p], ob[p + 1], lane, acc, [&](int ch, int e) { return rows[ch * rowlen + e]; });
+            pull_list_warp<CC>(pb, ob[p], ob[p + 1], lane, acc, [&](int ch, int e) { return contrib(rows, ch, e); });
             if (lane == 0) {
 #pragma unroll
                 for (int ch = 0; ch < CC; ++ch)
@@ -422,7 +435,7 @@ __global__ void __launch_bounds__(1024, 1) pull_stream_kernel(const float* __res
 
 template <int MODE>
 static int launch_pull_stream(const float* src, const int* offs, const int* pos, int b, int c, int ntargets, int rowlen, int k,
-                              float* dst, cudaStream_t st, bool* launched) {
+                              float* dst, cudaStream_t st, bool* launched, const float* wgt = nullptr) {
     *launched = false;
     const size_t row_bytes = (size_t)rowlen * 4;
     if ((rowlen & 3) != 0 || (reinterpret_cast<uintptr_t>(src) & 15) != 0 || 2 * row_bytes > 200 * 1024) return PDGN_OK;
@@ -438,7 +451,7 @@ static int launch_pull_stream(const float* src, const int* offs, const int* pos,
 #define PDGN_LAUNCH_PULL(CC_)                                                                                                   \
     do {                                                                                                                        \
         PDGN_CUDA(cudaFuncSetAttribute(pull_stream_kernel<CC_, MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
-        pull_stream_kernel<CC_, MODE><<<grid, 1024, smem, st>>>(src, offs, pos, c, ntargets, rowlen, k, cpc, dst);              \
+        pull_stream_kernel<CC_, MODE><<<grid, 1024, smem, st>>>(src, offs, pos, c, ntargets, rowlen, k, cpc, dst, wgt);         \
     } while (0)
     if (CCsel == 4) PDGN_LAUNCH_PULL(4);
     else if (CCsel == 2) PDGN_LAUNCH_PULL(2);
@@ -865,6 +878,12 @@ extern "C" int pdgn_interp_bwd_ws(const float* grad_out, const int* idx, const f
     PDGN_CUDA(cudaFuncSetAttribute(csr_build_kernel<int>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)csr_smem));
     csr_build_kernel<int><<<b, CSR_T, csr_smem, st>>>(idx, m, 3 * n, offs, pos);
     PDGN_CHECK_LAUNCH();
+    {   // streaming form (TMA double-buffered rows, register-cached lists and weights): any shape it accepts
+        bool launched = false;
+        const int rc = launch_pull_stream<2>(grad_out, offs, pos, b, c, m, n, 3, grad_points, st, &launched, weight);
+        if (rc != PDGN_OK) return rc;
+        if (launched) return PDGN_OK;
+    }
     PDGN_CUDA(cudaFuncSetAttribute(interp_bwd_pull_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     dim3 grid((c + cc - 1) / cc, b);
     interp_bwd_pull_kernel<<<grid, 512, smem, st>>>(grad_out, weight, offs, pos, c, n, m, cc, grad_points);
