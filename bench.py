@@ -221,8 +221,9 @@ def main():
     torch.cuda.set_device(local_rank)
     dev = torch.device("cuda", local_rank)
     if world > 1:
-        if os.environ.get("NCCL_DEBUG", "").upper() in ("", "VERSION"):
-            os.environ["NCCL_DEBUG"] = "WARN"  # keep stdout to the one JSON line (NCCL prints its version banner there)
+        # keep stdout to the one JSON line: NCCL writes its debug output (the version banner at WARN and above) to stdout
+        # unless told otherwise
+        os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
         dist.init_process_group("nccl", device_id=dev)
     from pdgn_b200 import _build
     if rank == 0:
@@ -246,11 +247,16 @@ def main():
         all_cd, _ = em._pairwise_EMD_CD_(smp_d, ref_d, 50)
         return all_cd
 
+    out_h = torch.empty((nc, nc), dtype=torch.float32).pin_memory()
+
     def step_e2e():
         # pinned HOST tensors straight into the public API: it copies what this rank's tile needs (everything at N=1, its
-        # rows + columns under torchrun) and returns the full matrix on the device; .cpu() is the D2H of the step's result
+        # rows + columns under torchrun) and returns the full matrix on the device; the copy into the pinned result buffer
+        # is the D2H of the step's result
         all_cd, _ = em._pairwise_EMD_CD_(smp_h, ref_h, 50)
-        return all_cd.cpu()
+        out_h.copy_(all_cd, non_blocking=True)
+        torch.cuda.current_stream().synchronize()
+        return out_h
 
     def sync_all():
         torch.cuda.synchronize()
