@@ -320,7 +320,7 @@ __global__ void __launch_bounds__(1024, 1) pull_stream_kernel(const float* __res
     const int nloc = min(nchunks, chunk0 + chunks_per_cta) - chunk0;
     if (nloc <= 0) return;
     const float* g0_b = src + (size_t)bz * 2 * c * rowlen;                                  // MODE 1 only
-    const float* rows_b = MODE == 0 ? src + (size_t)bz * c * rowlen : g0_b + (size_t)c * rowlen;
+    const float* rows_b = MODE != 1 ? src + (size_t)bz * c * rowlen : g0_b + (size_t)c * rowlen;
     float* dst_b = dst + (size_t)bz * c * ntargets;
     const int* ob = offs + (size_t)bz * (ntargets + 1);
     const int* pb = pos + (size_t)bz * rowlen * (MODE == 2 ? 3 : 1);

@@ -294,9 +294,10 @@ __global__ void __launch_bounds__(KQ_W * 32, 1) knn_gram_kernel(const float* __r
         unsigned long long* const ktop = reinterpret_cast<unsigned long long*>(blk + KQ_BLK) + lane;
         auto key_at = [&](int slot) -> unsigned long long& { return ktop[-32 * (slot + 1)]; };
         unsigned long long* kp = ktop;          // one slot above the next free one
-        // lowest slot address that stays clear of this lane's flag list (rows of 128 bytes, 4 entries of each lane per row)
-        const unsigned long long* const kfloor = reinterpret_cast<const unsigned long long*>(blk + ((nf + 3) >> 2) * 128) + 4 * 32;
         const int nfmax = __reduce_max_sync(kFull, nf);
+        // lowest slot address that stays clear of EVERY lane's flag list (a 256-byte key row spans all 32 lanes' columns of
+        // two 128-byte list rows, so the floor is the warp's longest list), plus the 4 slots a quad may add before the check
+        const unsigned long long* const kfloor = reinterpret_cast<const unsigned long long*>(blk + ((nfmax + 3) >> 2) * 128) + 4 * 32;
         float4 cx[SS / 4], cy[SS / 4], cz[SS / 4];
         int sg = nf > 0 ? (int)pl(0) : -1;
         {
