@@ -213,7 +213,7 @@ static int dispatch_nn_min(const float* x, const float* y, int b, int nx, int ny
 
 template <int D>
 static int nn_min_multi_launch_d(MinTable& tb, int b, cudaStream_t st) {
-    constexpr int S = D <= 8 ? 4 : 2;       // slices per CTA: the training shapes have few queries per batch element
+    constexpr int S = 4;                    // slices per CTA: the training shapes have few queries per batch element
     int ctas = 0;
     for (int i = 0; i < tb.count; ++i) {
         tb.p[i].cta0 = ctas;

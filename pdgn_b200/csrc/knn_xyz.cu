@@ -578,11 +578,10 @@ static int knn_dispatch(const float* xyz, const float* new_xyz, int b, int n, in
     return PDGN_OK;
 }
 
-int knn_multi_launch(KnnTable& tb, int b, int k, cudaStream_t st) {
-    // one instantiation for every problem: 64 groups, 16 warps = 4 query blocks x 4 candidate slices (the sliced form keeps
-    // the small query sets of the training shapes spread over many warps)
-    constexpr int G = 64, NWARPS = 16, S = 4, NQ = NWARPS / S;
-    if (k < 1 || k > 24 || tb.count < 1 || tb.count > 12) return PDGN_ERR_UNSUPPORTED;
+template <int S>
+static int knn_multi_launch_s(KnnTable& tb, int b, int k, cudaStream_t st) {
+    // one instantiation for every problem: 64 groups, 16 warps = 16/S query blocks x S candidate slices
+    constexpr int G = 64, NWARPS = 16, NQ = NWARPS / S;
     int ctas = 0;
     for (int i = 0; i < tb.count; ++i) {
         KnnProb& pr = tb.p[i];
@@ -596,6 +595,19 @@ int knn_multi_launch(KnnTable& tb, int b, int k, cudaStream_t st) {
     knn_select_multi_kernel<G, NWARPS, S><<<dim3(ctas, b), NWARPS * 32, smem, st>>>(tb, k);
     PDGN_CHECK_LAUNCH();
     return PDGN_OK;
+}
+
+int knn_multi_launch(KnnTable& tb, int b, int k, cudaStream_t st) {
+    if (k < 1 || k > 24 || tb.count < 1 || tb.count > 12) return PDGN_ERR_UNSUPPORTED;
+    // slices per query block: with all problems of a step in one grid the chip is full without slicing small query sets
+    // thinly; fewer slices = fewer copies of each candidate tile and fewer partial minima to merge
+    long long queries = 0;
+    for (int i = 0; i < tb.count; ++i) queries += tb.p[i].m;
+    static const char* force = tune_env("PDGN_KNN_MULTI_S");
+    const int s = force ? atoi(force) : (queries * b >= 148LL * 256 ? 2 : 4);   // measured at B=35: S=1 273 us, S=2 237 us, S=4 257 us
+    if (s == 1) return knn_multi_launch_s<1>(tb, b, k, st);
+    if (s == 2) return knn_multi_launch_s<2>(tb, b, k, st);
+    return knn_multi_launch_s<4>(tb, b, k, st);
 }
 
 }  // namespace pdgn
