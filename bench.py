@@ -616,7 +616,7 @@ def bench_cfg3(dev):
            "loss_side_launches": {"fwd": 6, "bwd": 5, "note": "pdgn_shape_loss_fwd/bwd: all 9 kNN / 9 statistics / 24 minimum problems of the "
                                   "step per operator launch; what the drop-in runs for the trainer's six get_local_pair calls"},
            "loss_side_per_call_fwd_ms": _ev_ms(lambda: loss_side(False)), "loss_side_per_call_fwd_bwd_ms": _ev_ms(lambda: loss_side(True))}
-    stages = {}
+    stages, feat_knn = {}, {}
     for c, n in [(32, 128), (64, 256), (128, 512), (256, 1024)]:
         x = torch.randn(B, c, n, device=dev)
         pc = torch.rand(B, 3, n, device=dev) * 2 - 1
@@ -627,7 +627,12 @@ def bench_cfg3(dev):
             (e_fea.sum() + e_xyz.sum()).backward()
 
         stages["C%d_N%d" % (c, n)] = _ev_ms(stage)
+        # the kNN kernel of the stage alone: exact FP32 direct distances, 2C FMA-pipe instructions per (query, candidate) pair
+        from pdgn_b200 import ops
+        kms = _ev_ms(lambda: ops.knn_feat(x, 10, skip=1))
+        feat_knn["C%d_N%d" % (c, n)] = {"ms": kms, "fp32_issue_frac": B * n * n * 2.0 * c / (kms * 1e-3) / (148 * 128 * 1.965e9)}
     res["edge_feature_stage_fwd_bwd_ms"] = stages
+    res["feature_knn"] = feat_knn
     try:
         from oracle import ref_tree
         if not ref_tree.available():
