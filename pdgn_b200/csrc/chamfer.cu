@@ -226,6 +226,7 @@ static int nn_min_multi_launch_d(MinTable& tb, int b, cudaStream_t st) {
 int nn_min_multi_launch(MinTable& tb, int b, int d, cudaStream_t st) {
     if (tb.count < 1 || tb.count > MULTI_MAX) return PDGN_ERR_UNSUPPORTED;
     if (d == 3) return nn_min_multi_launch_d<3>(tb, b, st);
+    if (d == 6) return nn_min_multi_launch_d<6>(tb, b, st);
     if (d == 9) return nn_min_multi_launch_d<9>(tb, b, st);
     return PDGN_ERR_UNSUPPORTED;
 }

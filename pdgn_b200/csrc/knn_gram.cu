@@ -234,14 +234,25 @@ __global__ void __launch_bounds__(KQ_W * 32, 1) knn_gram_kernel(const float* __r
                 const float4 y4 = *reinterpret_cast<const float4*>(Y + base + 4 * qd);
                 const float4 z4 = *reinterpret_cast<const float4*>(Z + base + 4 * qd);
                 const float4 p4 = *reinterpret_cast<const float4*>(P + base + 4 * qd);
+                // coordinate-major order: consecutive FFMAs share the candidate operand (register reuse cache), which is what lets
+                // a three-source FFMA issue near full rate (tools/knn_probe.cu: 90 % vs 80 % of the 6-instr roofline at R = 2)
+                const float xs[4] = {x4.x, x4.y, x4.z, x4.w}, ys[4] = {y4.x, y4.y, y4.z, y4.w};
+                const float zs[4] = {z4.x, z4.y, z4.z, z4.w}, ps[4] = {p4.x, p4.y, p4.z, p4.w};
+                float g[KQ_R][4];
 #pragma unroll
-                for (int r = 0; r < KQ_R; ++r) {
-                    const float g0 = __fmaf_rn(ax[r], x4.x, __fmaf_rn(ay[r], y4.x, __fmaf_rn(az[r], z4.x, p4.x)));
-                    const float g1 = __fmaf_rn(ax[r], x4.y, __fmaf_rn(ay[r], y4.y, __fmaf_rn(az[r], z4.y, p4.y)));
-                    const float g2 = __fmaf_rn(ax[r], x4.z, __fmaf_rn(ay[r], y4.z, __fmaf_rn(az[r], z4.z, p4.z)));
-                    const float g3 = __fmaf_rn(ax[r], x4.w, __fmaf_rn(ay[r], y4.w, __fmaf_rn(az[r], z4.w, p4.w)));
-                    mn[r] = min3(min3(mn[r], g0, g1), g2, g3);          // fminf drops NaN operands: padding never wins
-                }
+                for (int u = 0; u < 4; ++u)
+#pragma unroll
+                    for (int r = 0; r < KQ_R; ++r) g[r][u] = __fmaf_rn(az[r], zs[u], ps[u]);
+#pragma unroll
+                for (int u = 0; u < 4; ++u)
+#pragma unroll
+                    for (int r = 0; r < KQ_R; ++r) g[r][u] = __fmaf_rn(ay[r], ys[u], g[r][u]);
+#pragma unroll
+                for (int u = 0; u < 4; ++u)
+#pragma unroll
+                    for (int r = 0; r < KQ_R; ++r) g[r][u] = __fmaf_rn(ax[r], xs[u], g[r][u]);
+#pragma unroll
+                for (int r = 0; r < KQ_R; ++r) mn[r] = min3(min3(mn[r], g[r][0], g[r][1]), g[r][2], g[r][3]);   // fminf drops NaN: padding never wins
             }
 #pragma unroll
             for (int r = 0; r < KQ_R; ++r) {

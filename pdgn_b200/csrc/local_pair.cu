@@ -9,6 +9,7 @@
 // backward entry point reuses (indices, statistics, arg-minima), and nothing synchronises the host.
 #include <cstdint>
 #include "common.cuh"
+#include "multi.cuh"
 
 namespace pdgn {
 
@@ -111,11 +112,12 @@ extern "C" int pdgn_local_pair_fwd(const float* pt1, const float* pt2, int b, in
     // Gen_QueryAndGroupXYZ(pt1, pt1) and (pt2, pt1): the queries are pt1's points in both (PDGNet_v2.py:139-146)
     PDGN_LP_TRY(pdgn_knn_xyz(W + L.p1, W + L.p1, b, m, m, k, WI + L.idx1, nullptr, stream));
     PDGN_LP_TRY(pdgn_knn_xyz(W + L.p2, W + L.p1, b, n, m, k, WI + L.idx2, nullptr, stream));
-    PDGN_LP_TRY(pdgn_local_stats_fwd(W + L.p1, WI + L.idx1, b, m, m, k, W + L.mu1, W + L.cov1, stream));
-    PDGN_LP_TRY(pdgn_local_stats_fwd(W + L.p2, WI + L.idx2, b, n, m, k, W + L.mu2, W + L.cov2, stream));
+    // covariances in the packed 6-channel layout (local_stats.cu): same Frobenius distances, a third less Chamfer work
+    PDGN_LP_TRY(local_stats_fwd_launch(W + L.p1, WI + L.idx1, b, m, m, k, W + L.mu1, W + L.cov1, 6, st));
+    PDGN_LP_TRY(local_stats_fwd_launch(W + L.p2, WI + L.idx2, b, n, m, k, W + L.mu2, W + L.cov2, 6, st));
     // ChamferLoss(preds = stats of pt2, gts = stats of pt1): both directional minima (chamfer_loss.py:13-20)
     PDGN_LP_TRY(pdgn_chamfer_min(W + L.mu2, W + L.mu1, b, m, m, 3, W + L.mn[0], WI + L.mn[1], W + L.mn[2], WI + L.mn[3], stream));
-    PDGN_LP_TRY(pdgn_chamfer_min(W + L.cov2, W + L.cov1, b, m, m, 9, W + L.mn[4], WI + L.mn[5], W + L.mn[6], WI + L.mn[7], stream));
+    PDGN_LP_TRY(pdgn_chamfer_min(W + L.cov2, W + L.cov1, b, m, m, 6, W + L.mn[4], WI + L.mn[5], W + L.mn[6], WI + L.mn[7], stream));
     lp_sums_kernel<<<1, 1024, 0, st>>>(W + L.mn[0], W + L.mn[2], W + L.mn[4], W + L.mn[6], (size_t)b * m, 1.0f / (float)m, out);
     PDGN_CHECK_LAUNCH();
     return PDGN_OK;
@@ -136,10 +138,10 @@ extern "C" int pdgn_local_pair_bwd(int b, int m, int n, int k, const float* grad
     lp_fill_w_kernel<<<(unsigned)((2 * bm + 255) / 256), 256, 0, st>>>(grad_out, bm, 1.0f / (float)m, W + L.w);
     PDGN_CHECK_LAUNCH();
     PDGN_LP_TRY(pdgn_chamfer_bwd(W + L.mu2, W + L.mu1, b, m, m, 3, W + L.w, WI + L.mn[1], W + L.w, WI + L.mn[3], W + L.gmu2, W + L.gmu1, stream));
-    PDGN_LP_TRY(pdgn_chamfer_bwd(W + L.cov2, W + L.cov1, b, m, m, 9, W + L.w + bm, WI + L.mn[5], W + L.w + bm, WI + L.mn[7], W + L.gcov2,
+    PDGN_LP_TRY(pdgn_chamfer_bwd(W + L.cov2, W + L.cov1, b, m, m, 6, W + L.w + bm, WI + L.mn[5], W + L.w + bm, WI + L.mn[7], W + L.gcov2,
                                  W + L.gcov1, stream));
-    PDGN_LP_TRY(pdgn_local_stats_bwd(W + L.p1, WI + L.idx1, W + L.mu1, W + L.gmu1, W + L.gcov1, b, m, m, k, W + L.gp1, stream));
-    PDGN_LP_TRY(pdgn_local_stats_bwd(W + L.p2, WI + L.idx2, W + L.mu2, W + L.gmu2, W + L.gcov2, b, n, m, k, W + L.gp2, stream));
+    PDGN_LP_TRY(local_stats_bwd_launch(W + L.p1, WI + L.idx1, W + L.mu1, W + L.gmu1, W + L.gcov1, b, m, m, k, W + L.gp1, 6, st));
+    PDGN_LP_TRY(local_stats_bwd_launch(W + L.p2, WI + L.idx2, W + L.mu2, W + L.gmu2, W + L.gcov2, b, n, m, k, W + L.gp2, 6, st));
     lp_transpose_add_kernel<<<dim3((m + 255) / 256, b), 256, 0, st>>>(W + L.gp1, m, grad_pt1);
     PDGN_CHECK_LAUNCH();
     lp_transpose_add_kernel<<<dim3((n + 255) / 256, b), 256, 0, st>>>(W + L.gp2, n, grad_pt2);

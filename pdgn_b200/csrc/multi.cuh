@@ -32,10 +32,13 @@ __device__ __forceinline__ int multi_find(const Table& tb, int bx) {
 // knn_xyz.cu: every problem must satisfy 256 <= n <= 2048 (single resident tile) and k <= 24; returns PDGN_ERR_UNSUPPORTED
 // otherwise (the caller then falls back to one pdgn_knn_xyz call per problem).
 int knn_multi_launch(KnnTable& tb, int b, int k, cudaStream_t st);
-// local_stats.cu
+// local_stats.cu: the multi launches write / read the covariance in the packed 6-channel layout (see local_stats_fwd_body)
 int local_stats_multi_fwd(StatTable& tb, int b, int k, cudaStream_t st);
+int local_stats_fwd_launch(const float* xyz, const int* idx, int b, int n, int m, int k, float* mu, float* cov, int cw, cudaStream_t st);
+int local_stats_bwd_launch(const float* xyz, const int* idx, const float* mu, const float* grad_mu, const float* grad_cov, int b, int n,
+                           int m, int k, float* grad_xyz, int cw, cudaStream_t st);
 int local_stats_multi_bwd(StatTable& tb, int b, int k, cudaStream_t st);
-// chamfer.cu: all problems of one call share the channel count d (3 or 9 here)
+// chamfer.cu: all problems of one call share the channel count d (3, 6 or 9)
 int nn_min_multi_launch(MinTable& tb, int b, int d, cudaStream_t st);
 int chamfer_bwd_multi_launch(MinTable& tb, int b, int d, cudaStream_t st);
 

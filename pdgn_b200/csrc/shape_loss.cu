@@ -6,8 +6,9 @@
 // kNN problems, 9 statistics problems and 24 directional-minimum problems.  pdgn_local_pair_fwd (local_pair.cu) already put one
 // call behind one C entry point (11 launches); here every operator runs ALL its problems of the step from one descriptor
 // table (multi.cuh):
-//   forward : transpose x4 | kNN x9 | statistics x9 | minima d=3 x12 | minima d=9 x12 | 12 sums        = 6 launches
-//   backward: (memset) | Chamfer adjoint d=3 x12 | d=9 x12 | statistics adjoint x9 | transpose-add x4  = 4 launches
+//   forward : transpose x4 | kNN x9 | statistics x9 | minima d=3 x12 | minima d=6 x12 | 12 sums        = 6 launches
+//   backward: (memset) | Chamfer adjoint d=3 x12 | d=6 x12 | statistics adjoint x9 | transpose-add x4  = 4 launches
+// (d=6: the symmetric covariances travel packed as (xx, yy, zz, sqrt2 xy, sqrt2 xz, sqrt2 yz): same Frobenius distance, 6 channels)
 // Values are those of the per-call path (same kernels' bodies); the shared self statistics are computed once.
 #include <cstdint>
 #include "common.cuh"
@@ -158,7 +159,7 @@ extern "C" int pdgn_shape_loss_fwd(const float* const* pts, int b, int levels, c
         sums.inv_m[2 * p] = sums.inv_m[2 * p + 1] = inv_m;
     }
     PDGN_SL_TRY(nn_min_multi_launch(m3, b, 3, st));
-    PDGN_SL_TRY(nn_min_multi_launch(m9, b, 9, st));
+    PDGN_SL_TRY(nn_min_multi_launch(m9, b, 6, st));   // covariances in the packed 6-channel layout
     sl_sums_kernel<<<2 * L.pairs, 1024, 0, st>>>(sums, out);
     PDGN_CHECK_LAUNCH();
     return PDGN_OK;
@@ -187,7 +188,7 @@ extern "C" int pdgn_shape_loss_bwd(int b, int levels, const int* npts, int k, co
         m9.p[m9.count++] = MinProb{W + L.covS[a], W + L.covC[p], nullptr, WI + L.mn[p][7], W + L.gcovS[a], W + L.gcovC[p], gcv, inv_m, m, m, 0};
     }
     PDGN_SL_TRY(chamfer_bwd_multi_launch(m3, b, 3, st));
-    PDGN_SL_TRY(chamfer_bwd_multi_launch(m9, b, 9, st));
+    PDGN_SL_TRY(chamfer_bwd_multi_launch(m9, b, 6, st));
     StatTable stt{};
     for (int a = 0; a + 1 < levels; ++a)
         stt.p[stt.count++] = StatProb{W + L.P[a], WI + L.idxS[a], W + L.muS[a], nullptr, W + L.gP[a], W + L.gmuS[a], W + L.gcovS[a], npts[a], npts[a], 0};

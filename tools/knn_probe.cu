@@ -15,7 +15,7 @@ constexpr int PL = N + N / 32 * 4;  // padded plane
 
 __device__ __forceinline__ float min3(float a, float b, float c) { return fminf(fminf(a, b), c); }
 
-template <int R, bool GRAM>
+template <int R, bool GRAM, int ORDER = 0>
 __global__ void __launch_bounds__(512) pass1_probe(const float* __restrict__ pts, float* __restrict__ out, long long* cyc, int reps) {
     extern __shared__ __align__(16) float sm[];
     float* X = sm; float* Y = sm + PL; float* Z = sm + 2 * PL; float* P = sm + 3 * PL;
@@ -50,6 +50,24 @@ __global__ void __launch_bounds__(512) pass1_probe(const float* __restrict__ pts
                 const float4 z4 = *reinterpret_cast<const float4*>(Z + base + 4 * qd);
                 float4 p4 = make_float4(0, 0, 0, 0);
                 if (GRAM) p4 = *reinterpret_cast<const float4*>(P + base + 4 * qd);
+                if (GRAM && ORDER == 1) {
+                    const float xs[4] = {x4.x, x4.y, x4.z, x4.w}, ys[4] = {y4.x, y4.y, y4.z, y4.w}, zs[4] = {z4.x, z4.y, z4.z, z4.w}, ps[4] = {p4.x, p4.y, p4.z, p4.w};
+                    float g[R][4];
+#pragma unroll
+                    for (int u = 0; u < 4; ++u)
+#pragma unroll
+                        for (int r = 0; r < R; ++r) g[r][u] = fmaf(qz[r], zs[u], ps[u]);
+#pragma unroll
+                    for (int u = 0; u < 4; ++u)
+#pragma unroll
+                        for (int r = 0; r < R; ++r) g[r][u] = fmaf(qy[r], ys[u], g[r][u]);
+#pragma unroll
+                    for (int u = 0; u < 4; ++u)
+#pragma unroll
+                        for (int r = 0; r < R; ++r) g[r][u] = fmaf(qx[r], xs[u], g[r][u]);
+#pragma unroll
+                    for (int r = 0; r < R; ++r) m[r] = min3(min3(m[r], g[r][0], g[r][1]), g[r][2], g[r][3]);
+                } else
 #pragma unroll
                 for (int r = 0; r < R; ++r) {
                     float g0, g1, g2, g3;
@@ -68,7 +86,7 @@ __global__ void __launch_bounds__(512) pass1_probe(const float* __restrict__ pts
 #pragma unroll
             for (int r = 0; r < R; ++r) {
                 const float v = fmaxf(GRAM ? m[r] + qq[r] : m[r], 0.f);
-                subs[(r * 128 + sg) * 32] = (unsigned short)(__float_as_uint(v) >> 16);
+                if (R <= 4) subs[(r * 128 + sg) * 32] = (unsigned short)(__float_as_uint(v) >> 16);
                 acc[r] += v;
             }
         }
@@ -81,23 +99,23 @@ __global__ void __launch_bounds__(512) pass1_probe(const float* __restrict__ pts
     if (threadIdx.x == 0) cyc[blockIdx.x] = t1 - t0;
 }
 
-template <int R, bool GRAM>
+template <int R, bool GRAM, int ORDER = 0>
 int run_pass1(int warps, int nsm, const float* pts) {
     float* out; long long* cyc;
     const int reps = 8;
     CK(cudaMalloc(&out, sizeof(float) * nsm * 512)); CK(cudaMalloc(&cyc, sizeof(long long) * nsm));
-    const size_t smem = (size_t)4 * PL * 4 + (size_t)warps * 128 * 32 * R * 2;
-    CK(cudaFuncSetAttribute(pass1_probe<R, GRAM>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    pass1_probe<R, GRAM><<<nsm, warps * 32, smem>>>(pts, out, cyc, reps);
+    const size_t smem = (size_t)4 * PL * 4 + (size_t)warps * 128 * 32 * (R <= 4 ? R : 1) * 2;
+    CK(cudaFuncSetAttribute(pass1_probe<R, GRAM, ORDER>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    pass1_probe<R, GRAM, ORDER><<<nsm, warps * 32, smem>>>(pts, out, cyc, reps);
     CK(cudaDeviceSynchronize());
-    pass1_probe<R, GRAM><<<nsm, warps * 32, smem>>>(pts, out, cyc, reps);
+    pass1_probe<R, GRAM, ORDER><<<nsm, warps * 32, smem>>>(pts, out, cyc, reps);
     CK(cudaDeviceSynchronize());
     long long* h = new long long[nsm]; CK(cudaMemcpy(h, cyc, sizeof(long long) * nsm, cudaMemcpyDeviceToHost));
     double mean = 0; for (int i = 0; i < nsm; ++i) mean += h[i]; mean /= nsm;
     const double pairs_per_sm = (double)reps * N * warps * 32 * R;     // (query, candidate) pairs
     // lane-pairs per cycle per SM; the FP32 peak is 128 lane-instr/cycle/SM => pairs/cycle at the 6-instr roofline = 21.3
-    printf("pass1 %-6s R=%d warps/SM=%2d  smem %6zu B  cycles %9.0f  pairs/cycle/SM %6.2f  = %5.1f %% of the 6-instr/pair roofline (21.33)\n",
-           GRAM ? "gram" : "direct", R, warps, smem, mean, pairs_per_sm / mean, 100.0 * pairs_per_sm / mean / (128.0 / 6.0));
+    printf("pass1 %-6s order=%d R=%2d warps/SM=%2d  smem %6zu B  cycles %9.0f  pairs/cycle/SM %6.2f  = %5.1f %% of the 6-instr/pair roofline (21.33)\n",
+           GRAM ? "gram" : "direct", ORDER, R, warps, smem, mean, pairs_per_sm / mean, 100.0 * pairs_per_sm / mean / (128.0 / 6.0));
     cudaFree(out); cudaFree(cyc); delete[] h; return 0;
 }
 
@@ -164,6 +182,10 @@ int main() {
     unsigned s = 12345;
     for (int i = 0; i < 3 * N; ++i) { s = s * 1664525u + 1013904223u; h[i] = (float)(s >> 8) / 8388608.0f - 1.0f; }
     float* pts; CK(cudaMalloc(&pts, sizeof(float) * 3 * N)); CK(cudaMemcpy(pts, h, sizeof(float) * 3 * N, cudaMemcpyHostToDevice));
+    for (int w = 4; w <= 8; w *= 2) {
+        run_pass1<2, true, 1>(w, nsm, pts); run_pass1<4, true, 1>(w, nsm, pts); run_pass1<8, true, 1>(w, nsm, pts); run_pass1<16, true, 1>(w, nsm, pts);
+        run_pass1<8, true, 0>(w, nsm, pts); run_pass1<16, true, 0>(w, nsm, pts); run_pass1<8, false, 0>(w, nsm, pts); run_pass1<16, false, 0>(w, nsm, pts);
+    }
     for (int w = 4; w <= 16; w *= 2) {
         run_pass1<1, false>(w, nsm, pts); run_pass1<2, false>(w, nsm, pts); if (w <= 8) run_pass1<4, false>(w, nsm, pts);
         run_pass1<1, true>(w, nsm, pts);  run_pass1<2, true>(w, nsm, pts);  if (w <= 8) run_pass1<4, true>(w, nsm, pts);
