@@ -12,7 +12,7 @@ is 2-D tiled (pdgn_b200.dist) and the per-pair scalars are all-gathered over NCC
 One JSON line on rank 0:
   value          cloud pairs/s, device-resident inputs, CUDA events on the launch stream, max over ranks
   e2e            same metric through the public API (_pairwise_EMD_CD_) from pinned HOST tensors, H2D + D2H inside
-  roofline       FP32-SIMT roofline of the dominant kernel (cd_allpairs_kernel): 6 FMA-pipe instructions per point pair
+  roofline       FP32-SIMT roofline of the dominant kernel (cd_gram_kernel): 6 FMA-pipe instructions per point pair
   cpu_baseline   the reference's CPU formulation (oracle.torch_ref.pairwise_cd = distChamfer loop) on a bounded sample
   knnquery       secondary metric of BASELINE.json (Mqueries/s, k=20, B=35 x 2048) measured in the same run
   reference_gpu  "reference on B200" (SURVEY.md 8d): the reference's torch Gram-form distChamfer loop and its NNDistance
@@ -157,7 +157,7 @@ def cpu_reference_rate(n_sample, n_ref, repeats=1):
 
 
 def traffic_from_profile(nc, world):
-    """DRAM bytes (read+write) of one cd_allpairs_kernel launch from the committed ncu --set full capture
+    """DRAM bytes (read+write) of one launch of the dominant kernel from the committed ncu --set full capture
     (profiles/cd_allpairs_traffic.json); only valid for the configuration that was captured (1000 clouds, 1 GPU)."""
     if nc != N_CLOUDS or world != 1:
         return None
@@ -341,13 +341,17 @@ def main():
     achieved_tflops = 2.0 * inst_rate / 1e12                      # each FMA-pipe instruction = one FMA slot (2 FLOP)
     obs_mhz = (clocks or {}).get("sm_mhz") or sm_max_mhz
     roofline = {
-        "bound": "fp32", "kernel": "cd_allpairs_kernel", "achieved": achieved_tflops, "peak": peak_tflops, "unit": "TFLOP/s",
+        "bound": "fp32", "kernel": "cd_gram_kernel", "achieved": achieved_tflops, "peak": peak_tflops, "unit": "TFLOP/s",
         "frac": achieved_tflops / peak_tflops,
         # dram__bytes_read.sum + dram__bytes_write.sum of one launch (bytes), or null outside the captured configuration
         "traffic": (traffic_from_profile(nc, world) or {}).get("bytes"), "traffic_detail": traffic_from_profile(nc, world),
         "kernel_ms": kernel_ms, "cloud_pairs_per_launch": tile_pairs,
-        "definition": "achieved = cloud pairs x 2048^2 point pairs x 6 FMA-pipe instr x 2 FLOP-slots / kernel time (issue-rate "
-                      "fraction == FMA-pipe utilisation, SURVEY.md 8d); peak = SMs x 128 lanes x 2 x sm_max_mhz (MEASURED_PEAKS.json)",
+        "definition": "achieved = cloud pairs x 2048^2 point pairs x 6 FMA-pipe instr x 2 FLOP-slots / kernel time (the ALGORITHMIC "
+                      "work of SURVEY.md 8d: the direct-form distance); peak = SMs x 128 lanes x 2 x sm_max_mhz (MEASURED_PEAKS.json)",
+        "executed": "the kernel computes |a|^2 + |b|^2 - 2a.b (the reference's own default arithmetic): 3 three-source FFMA + 1 FADD per pair "
+                    "+ 1.0 min3, 5.4 SASS instr per pair; PDGN_B200_CD_EXACT=1 runs the 6-instruction direct form (bit-identical minima to "
+                    "NmDistanceKernel) at ~0.70",
+        "frac_of_executed_fma_pipe_instr": tile_pairs * POINT_PAIRS_PER_CLOUD_PAIR * 4 / (kernel_ms * 1e-3) / (lanes * sm_max_mhz * 1e6),
         "flop_frac": tile_pairs * POINT_PAIRS_PER_CLOUD_PAIR * FLOP_PER_POINT_PAIR / (kernel_ms * 1e-3) / 1e12 / peak_tflops,
         "frac_at_observed_clock": achieved_tflops / (2.0 * lanes * obs_mhz * 1e6 / 1e12),
         "sms": props.multi_processor_count,
@@ -363,7 +367,9 @@ def main():
                 "h2d_bytes_per_step": world * ((rows[1] - rows[0]) + (cols[1] - cols[0])) * N_PTS * 3 * 4, "d2h_bytes_per_step": nc * nc * 4,
                 "h2d_note": "summed over ranks: each rank copies only the rows + columns of its tile",
                 "api": "pdgn_b200.evaluation_metrics._pairwise_EMD_CD_(pinned host tensors) (PDGN_B200_SKIP_EMD=1: CD half) + .cpu()"},
-        "gpu_launches": 3 * args.steps,
+        # per step: 2 direct-form packs + 2 Gram-form packs + scale + gate + the direct-form kernel (returns at once when the gate
+        # picks the Gram form) + the Gram-form kernel
+        "gpu_launches": 8 * args.steps,
         "roofline": roofline, "clocks": clocks,
     }
     if not args.no_extras:

@@ -36,16 +36,36 @@ constexpr int CD_THREADS = CD_NH * CD_HALF;
 
 template <int VAR>
 static int cd_launch(bool sym, dim3 grid, size_t smem, cudaStream_t st, const float* PA, const float* PB, int nrows, int ncols,
-                     int npts, int npad, int rstrip, float* out, long long ld_out) {
+                     int npts, int npad, int rstrip, float* out, long long ld_out, const unsigned* gate) {
     if (sym) {
         PDGN_CUDA(cudaFuncSetAttribute(cd_allpairs_kernel<CD_R, CD_NH, CD_MINB, VAR, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        cd_allpairs_kernel<CD_R, CD_NH, CD_MINB, VAR, true><<<grid, CD_THREADS, smem, st>>>(PA, PB, nrows, ncols, npts, npad, rstrip, out, ld_out);
+        cd_allpairs_kernel<CD_R, CD_NH, CD_MINB, VAR, true><<<grid, CD_THREADS, smem, st>>>(PA, PB, nrows, ncols, npts, npad, rstrip, out, ld_out, gate);
     } else {
         PDGN_CUDA(cudaFuncSetAttribute(cd_allpairs_kernel<CD_R, CD_NH, CD_MINB, VAR, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        cd_allpairs_kernel<CD_R, CD_NH, CD_MINB, VAR, false><<<grid, CD_THREADS, smem, st>>>(PA, PB, nrows, ncols, npts, npad, rstrip, out, ld_out);
+        cd_allpairs_kernel<CD_R, CD_NH, CD_MINB, VAR, false><<<grid, CD_THREADS, smem, st>>>(PA, PB, nrows, ncols, npts, npad, rstrip, out, ld_out, gate);
     }
     PDGN_CHECK_LAUNCH();
     return PDGN_OK;
+}
+
+static int cdg_launch(bool sym, dim3 grid, size_t smem, cudaStream_t st, const float* PA, const float* PB, int nrows, int ncols,
+                      int npts, int npad, int rstrip, float* out, long long ld_out, const unsigned* gate) {
+    if (sym) {
+        PDGN_CUDA(cudaFuncSetAttribute(cd_gram_kernel<CD_R, CD_NH, CD_MINB, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        cd_gram_kernel<CD_R, CD_NH, CD_MINB, true><<<grid, CD_THREADS, smem, st>>>(PA, PB, nrows, ncols, npts, npad, rstrip, out, ld_out, gate);
+    } else {
+        PDGN_CUDA(cudaFuncSetAttribute(cd_gram_kernel<CD_R, CD_NH, CD_MINB, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        cd_gram_kernel<CD_R, CD_NH, CD_MINB, false><<<grid, CD_THREADS, smem, st>>>(PA, PB, nrows, ncols, npts, npad, rstrip, out, ld_out, gate);
+    }
+    PDGN_CHECK_LAUNCH();
+    return PDGN_OK;
+}
+
+// PDGN_B200_CD_EXACT=1 (a product switch, read once): every tile uses the direct-form kernel, whose minima are bit-identical to
+// the reference's NmDistanceKernel; by default centred clouds of <= 2048 points take the Gram-form kernel (cd_kernel.cuh).
+static bool cd_exact_only() {
+    static const bool on = [] { const char* e = getenv("PDGN_B200_CD_EXACT"); return e && e[0] == '1'; }();
+    return on;
 }
 
 static int cd_num_sms() {
@@ -66,7 +86,8 @@ using namespace pdgn;
 
 extern "C" size_t pdgn_cd_allpairs_workspace(int na, int nb, int npts) {
     if (na < 0 || nb < 0 || npts <= 0) return 0;
-    return ((size_t)na + (size_t)nb) * 3 * (size_t)cd_npad(npts) * sizeof(float) + 256;
+    // 3 planes per cloud for the direct-form kernel + 4 for the Gram-form one + the gate words
+    return ((size_t)na + (size_t)nb) * 7 * (size_t)cd_npad(npts) * sizeof(float) + 512;
 }
 
 extern "C" int pdgn_cd_allpairs(const float* A, const float* B, int na, int nb, int npts, int row0, int row1, int col0,
@@ -81,12 +102,16 @@ extern "C" int pdgn_cd_allpairs(const float* A, const float* B, int na, int nb, 
     if (!A || !B || !out) return PDGN_ERR_BAD_ARG;
     if (ld_out < ncols) return PDGN_ERR_BAD_ARG;
     const int npad = cd_npad(npts);
-    const size_t need = ((size_t)nrows + ncols) * 3 * npad * sizeof(float);
+    const bool gram = npts <= CD_R * CD_HALF && !cd_exact_only();   // Gram-form kernel eligible (the gate still decides per tile)
+    const size_t need = ((size_t)nrows + ncols) * (gram ? 7 : 3) * npad * sizeof(float) + (gram ? 256 : 0);
     if (!workspace || workspace_bytes < need) return PDGN_ERR_WORKSPACE;
     if ((reinterpret_cast<uintptr_t>(workspace) & 15) != 0) return PDGN_ERR_BAD_ARG;
     cudaStream_t st = (cudaStream_t)stream;
     float* PA = reinterpret_cast<float*>(workspace);
     float* PB = PA + (size_t)nrows * 3 * npad;
+    float* GA = PB + (size_t)ncols * 3 * npad;                       // Gram-form packs: [cloud][4][npad]
+    float* GB = GA + (size_t)nrows * 4 * npad;
+    unsigned* stats = reinterpret_cast<unsigned*>(GB + (size_t)ncols * 4 * npad);   // [0] max |p|^2, [1] mean NN d^2, [2] gate
 
     // same set against itself (the rr / ss matrices of compute_all_metrics, evaluation_metrics.py:187-188): pack once,
     // compute the upper triangle, mirror it
@@ -99,6 +124,23 @@ extern "C" int pdgn_cd_allpairs(const float* A, const float* B, int na, int nb, 
     } else {
         cd_pack_kernel<<<pgb, pb, 0, st>>>(B, col0, npts, npad, PB);
         PDGN_CHECK_LAUNCH();
+    }
+    const unsigned* gate = nullptr;
+    if (gram) {
+        PDGN_CUDA(cudaMemsetAsync(stats, 0, 3 * sizeof(unsigned), st));
+        cd_pack_gram_kernel<<<pga, pb, 0, st>>>(A, row0, npts, npad, GA, stats);
+        PDGN_CHECK_LAUNCH();
+        if (sym) {
+            GB = GA;
+        } else {
+            cd_pack_gram_kernel<<<pgb, pb, 0, st>>>(B, col0, npts, npad, GB, stats);
+            PDGN_CHECK_LAUNCH();
+        }
+        cd_scale_kernel<<<1, 256, 0, st>>>(A, row0, npts, stats);
+        PDGN_CHECK_LAUNCH();
+        cd_gate_kernel<<<1, 1, 0, st>>>(stats, npts, stats + 2);
+        PDGN_CHECK_LAUNCH();
+        gate = stats + 2;
     }
 
     const int spairs = (nrows + CD_NH - 1) / CD_NH;
@@ -118,11 +160,16 @@ extern "C" int pdgn_cd_allpairs(const float* A, const float* B, int na, int nb, 
     const dim3 grid(strips, spairs);
     static const bool force_big = tune_env("PDGN_CD_ATOMIC_COLMIN") != nullptr;  // tuning hook: the shared-atomic variant for every size
     int rc;
+    // two launches, one of which returns at once: the gate is decided on the device, the host never waits for it
     if (npts <= CD_R * CD_HALF && !force_big)
-        rc = cd_launch<CD_VARIANT>(sym, grid, cd_smem_bytes<CD_NH, CD_VARIANT>(npad), st, PA, PB, nrows, ncols, npts, npad, rstrip, out, ld_out);
+        rc = cd_launch<CD_VARIANT>(sym, grid, cd_smem_bytes<CD_NH, CD_VARIANT>(npad), st, PA, PB, nrows, ncols, npts, npad, rstrip, out, ld_out, gate);
     else
-        rc = cd_launch<CD_VARIANT_BIG>(sym, grid, cd_smem_bytes<CD_NH, CD_VARIANT_BIG>(npad), st, PA, PB, nrows, ncols, npts, npad, rstrip, out, ld_out);
+        rc = cd_launch<CD_VARIANT_BIG>(sym, grid, cd_smem_bytes<CD_NH, CD_VARIANT_BIG>(npad), st, PA, PB, nrows, ncols, npts, npad, rstrip, out, ld_out, gate);
     if (rc != PDGN_OK) return rc;
+    if (gram) {
+        rc = cdg_launch(sym, grid, cdg_smem_bytes<CD_NH>(npad), st, GA, GB, nrows, ncols, npts, npad, rstrip, out, ld_out, gate);
+        if (rc != PDGN_OK) return rc;
+    }
     if (sym) {
         cd_mirror_kernel<<<dim3((nrows + 31) / 32, (nrows + 7) / 8), dim3(32, 8), 0, st>>>(out, nrows, ld_out);
         PDGN_CHECK_LAUNCH();

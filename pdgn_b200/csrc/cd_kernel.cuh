@@ -136,8 +136,9 @@ __device__ __forceinline__ void cd_two_candidates_aos(const float (&qx)[R], cons
 template <int R, int NH, int MINB, int VAR, bool SYM = false>
 __global__ void __launch_bounds__(NH * CD_HALF, MINB)
 cd_allpairs_kernel(const float* __restrict__ PA, const float* __restrict__ PB, int nrows, int ncols, int npts, int npad,
-                   int rstrip, float* __restrict__ out, long long ld_out) {
+                   int rstrip, float* __restrict__ out, long long ld_out, const unsigned* __restrict__ gate = nullptr) {
     constexpr int ROWS = R * CD_HALF;
+    if (gate && *gate != 0u) return;  // the Gram-form kernel takes this tile (cd_gate_kernel)
     extern __shared__ __align__(128) unsigned char smem_raw[];
     constexpr int STAGE = ((VAR & CDV_AOS) ? 4 : 3) * CD_TILE;                // floats per stage
     float* tile = reinterpret_cast<float*>(smem_raw);                         // [2 stages][3 planes][CD_TILE] or [2][CD_TILE] float4
@@ -286,6 +287,229 @@ cd_allpairs_kernel(const float* __restrict__ PA, const float* __restrict__ PB, i
             out[(size_t)s * ld_out + r] = (rr[0] + rr[1] + rr[2] + rr[3]) * inv_n;
         }
     }
+}
+
+// =====================================================================================================
+// Gram-form variant (round 2): e_ij = |a_i|^2 - 2 a_i.b_j as THREE FFMAs on precomputed coefficients instead of the six
+// instructions of the reference chain; d_ij = e_ij + |b_j|^2.  The column minimum is taken on e (|b_j|^2 is added once per
+// column when the pair is folded), the row minimum on e + |b_j|^2 (one FADD per pair).  Measured with tools/cd_probe.cu: 84 %
+// of the 6-instruction roofline against 68 % for the direct form in the same loop.  This is the arithmetic of the reference's
+// own default path (torch bmm Gram form, evaluation_metrics.py:35-45) and meets its 1e-5 contract, but it is not the
+// bit pattern of NmDistanceKernel: the direct-form kernel above stays (PDGN_B200_CD_EXACT=1, clouds of more than 2048
+// points, and every tile whose clouds are not centred -- see cd_gate_kernel).
+// =====================================================================================================
+constexpr int CDG_TILE = 1024;   // candidates per stage: 2 stages x 4 planes x 4 KB = 32 KB (+ 64 KB of column arrays: 2 CTAs per SM)
+
+// AoS [cloud][npts][3] -> planes [cloud][4][npad]: x, y, z, |p|^2 (fma chain); pad entries replicate point 0.  Also the
+// largest |p|^2 of everything packed (stats[0], float bits, atomicMax: all values >= 0).
+__global__ void cd_pack_gram_kernel(const float* __restrict__ src, int cloud0, int npts, int npad, float* __restrict__ dst,
+                                    unsigned* __restrict__ stats) {
+    const int cl = blockIdx.y;
+    const int j = blockIdx.x * blockDim.x + threadIdx.x;
+    float pp = 0.f;
+    if (j < npad) {
+        const float* p = src + ((size_t)(cloud0 + cl) * npts + (j < npts ? j : 0)) * 3;
+        const float x = p[0], y = p[1], z = p[2];
+        pp = __fmaf_rn(z, z, __fmaf_rn(y, y, __fmul_rn(x, x)));
+        float* d = dst + (size_t)cl * 4 * npad + j;
+        d[0] = x;
+        d[npad] = y;
+        d[2 * (size_t)npad] = z;
+        d[3 * (size_t)npad] = pp;
+    }
+    // NaN / inf coordinates: report +inf so that the gate sends the tile to the direct-form kernel
+    unsigned bits = (pp <= 3.402823466e+38f) ? __float_as_uint(pp) : CD_INF_BITS;
+    bits = __reduce_max_sync(kFull, bits);
+    if ((threadIdx.x & 31) == 0) atomicMax(stats, bits);
+}
+
+// stats[1] = mean nearest-neighbour squared distance INSIDE cloud `cloud` of `src`, estimated on 64 evenly spaced sample points
+// (one CTA of 8 warps; warp w takes samples w, w+8, ...; the point itself is skipped, a duplicate gives 0).  It sets the scale of
+// the pair scalars the Gram form's rounding error has to be measured against.
+__global__ void __launch_bounds__(256) cd_scale_kernel(const float* __restrict__ src, int cloud, int npts, unsigned* __restrict__ stats) {
+    __shared__ float part[8];
+    const float* p = src + (size_t)cloud * npts * 3;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int nsamp = npts < 64 ? npts : 64;
+    float acc = 0.f;
+    for (int sidx = warp; sidx < nsamp; sidx += 8) {
+        const int i = (int)(((long long)sidx * npts) / nsamp);
+        const float qx = p[3 * i], qy = p[3 * i + 1], qz = p[3 * i + 2];
+        float best = kInf;
+        for (int j = lane; j < npts; j += 32)
+            if (j != i) best = fminf(best, d2_xyz(qx, qy, qz, p[3 * j], p[3 * j + 1], p[3 * j + 2]));
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) best = fminf(best, __shfl_xor_sync(kFull, best, o));
+        acc += best <= 3.402823466e+38f ? best : 0.f;   // a one-point or non-finite cloud counts as scale 0 => direct form
+    }
+    if (lane == 0) part[warp] = acc;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        float t = 0.f;
+        for (int w = 0; w < 8; ++w) t += part[w];
+        stats[1] = __float_as_uint(t / (float)nsamp);
+    }
+}
+
+// gate = 1: the Gram-form kernel computes this tile; 0: the direct-form kernel.  The Gram form's rounding error per distance
+// is ~3u(|a|^2 + |b|^2) <= 6u R^2 (u = 2^-24, R^2 = largest |p|^2 of the tile); it averages as a random walk over the 2 npts
+// minima of a pair, whose scalar is ~2 dmean (dmean = mean nearest-neighbour d^2, estimated by cd_scale_kernel):
+//     predicted relative error = 3u R^2 / (sqrt(2 npts) dmean)
+// (measured / predicted on tools/cd_check.py: sphere 1.2e-6 / 1.2e-6, cube 2.2e-7 / 6e-7, thin plane 6.7e-6 / 9e-6).  The Gram
+// form runs when the prediction is <= 3e-6, a third of the 1e-5 contract: every normalised shape set; clouds far from the
+// origin, scattered positions, near-planar / near-linear sets with tiny neighbour distances and non-finite coordinates take
+// the direct form.
+__global__ void cd_gate_kernel(const unsigned* __restrict__ stats, int npts, unsigned* __restrict__ gate) {
+    const float rmax2 = __uint_as_float(stats[0]), dmean = __uint_as_float(stats[1]);
+    const float pred = 3.f * 5.9604645e-8f * rmax2 / (sqrtf(2.f * (float)npts) * dmean);   // inf / NaN for dmean == 0 or non-finite data
+    *gate = (pred <= 3e-6f) ? 1u : 0u;
+}
+
+__device__ __forceinline__ int cdg_key(float v) {  // order-preserving float -> signed int (e can be negative); an involution
+    const int b = __float_as_int(v);
+    return b ^ ((b >> 31) & 0x7fffffff);
+}
+
+// Two candidates against the thread's R rows (Gram form): row minima on e + bb, column partial minima on e.
+template <int R>
+__device__ __forceinline__ void cdg_two_candidates(const float (&ax)[R], const float (&ay)[R], const float (&az)[R], const float (&aa)[R],
+                                                   float (&rowmin)[R], float x0, float y0, float z0, float b0, float x1, float y1,
+                                                   float z1, float b1, float& c0, float& c1) {
+    c0 = kInf;
+    c1 = kInf;
+#pragma unroll
+    for (int k = 0; k < R; k += 2) {
+        const float e00 = __fmaf_rn(ax[k], x0, __fmaf_rn(ay[k], y0, __fmaf_rn(az[k], z0, aa[k])));
+        const float e01 = __fmaf_rn(ax[k], x1, __fmaf_rn(ay[k], y1, __fmaf_rn(az[k], z1, aa[k])));
+        const float e10 = __fmaf_rn(ax[k + 1], x0, __fmaf_rn(ay[k + 1], y0, __fmaf_rn(az[k + 1], z0, aa[k + 1])));
+        const float e11 = __fmaf_rn(ax[k + 1], x1, __fmaf_rn(ay[k + 1], y1, __fmaf_rn(az[k + 1], z1, aa[k + 1])));
+        rowmin[k] = min3(rowmin[k], __fadd_rn(e00, b0), __fadd_rn(e01, b1));
+        rowmin[k + 1] = min3(rowmin[k + 1], __fadd_rn(e10, b0), __fadd_rn(e11, b1));
+        c0 = min3(c0, e00, e10);
+        c1 = min3(c1, e01, e11);
+    }
+}
+
+// Same CTA shape as cd_allpairs_kernel (NH halves of 128 threads, R rows per thread, one row block: npts <= R*128), per-warp
+// column arrays (plain STS.128 of four CREDUX results, no atomics).  PA / PB: [cloud][4][npad] from cd_pack_gram_kernel.
+template <int R, int NH, int MINB, bool SYM>
+__global__ void __launch_bounds__(NH * CD_HALF, MINB)
+cd_gram_kernel(const float* __restrict__ PA, const float* __restrict__ PB, int nrows, int ncols, int npts, int npad, int rstrip,
+               float* __restrict__ out, long long ld_out, const unsigned* __restrict__ gate) {
+    if (gate && *gate == 0u) return;  // the direct-form kernel takes this tile
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    constexpr int STAGE = 4 * CDG_TILE;
+    float* tile = reinterpret_cast<float*>(smem_raw);                       // [2 stages][4 planes][CDG_TILE]
+    int* colmin = reinterpret_cast<int*>(tile + 2 * STAGE);                 // [NH][4 warps][npad] signed keys of e
+    float* red = reinterpret_cast<float*>(colmin + NH * 4 * (size_t)npad);  // [NH][4 warps]
+    uint64_t* bars = reinterpret_cast<uint64_t*>(red + NH * 4);             // [2 stages]
+
+    const int tid = threadIdx.x, half = tid >> 7, ht = tid & (CD_HALF - 1), lane = tid & 31, hw = ht >> 5;
+    int s = blockIdx.y * NH + half;
+    const bool s_valid = s < nrows;
+    if (!s_valid) s = nrows - 1;
+    const int r_begin = SYM ? max((int)(blockIdx.x * rstrip), (int)(blockIdx.y * NH)) : blockIdx.x * rstrip;
+    const int r_end = min(ncols, (int)(blockIdx.x * rstrip) + rstrip);
+    if (SYM && r_begin >= r_end) return;
+    const int ncb = (npad + CDG_TILE - 1) / CDG_TILE;
+    const int ntiles = (r_end - r_begin) * ncb;
+    int* halfcol = colmin + (size_t)half * 4 * npad;
+    int* mycol = halfcol + (size_t)hw * npad;
+
+    if (tid == 0) {
+        mbar_init(&bars[0], 1);
+        mbar_init(&bars[1], 1);
+        mbar_fence_init();
+    }
+    __syncthreads();
+    auto issue = [&](int t) {
+        const int cb = t % ncb;
+        const int r = r_begin + t / ncb;
+        const int c0 = cb * CDG_TILE;
+        const unsigned bytes = (unsigned)min(CDG_TILE, npad - c0) * 4u;
+        uint64_t* bar = &bars[t & 1];
+        float* dst = tile + (t & 1) * STAGE;
+        const float* src = PB + (size_t)r * 4 * npad + c0;
+        mbar_expect_tx(bar, 4u * bytes);
+#pragma unroll
+        for (int pl = 0; pl < 4; ++pl) bulk_g2s(dst + pl * CDG_TILE, src + pl * (size_t)npad, bytes, bar);
+    };
+    if (tid == 0) {
+        issue(0);
+        if (ntiles > 1) issue(1);
+    }
+
+    // this thread's R rows of cloud s: coefficients -2a and |a|^2 (rows beyond npts replicate point 0 and are not summed)
+    float ax[R], ay[R], az[R], aa[R], rowmin[R];
+    {
+        const float* arow = PA + (size_t)s * 4 * npad;
+        const int i0 = ht * R;
+#pragma unroll
+        for (int k = 0; k < R; ++k) {
+            const int i = (i0 + k < npts) ? i0 + k : 0;
+            ax[k] = -2.f * arow[i];
+            ay[k] = -2.f * arow[npad + i];
+            az[k] = -2.f * arow[2 * (size_t)npad + i];
+            aa[k] = arow[3 * (size_t)npad + i];
+        }
+    }
+    const float inv_n = 1.0f / (float)npts;
+    const int nvalid = npts - ht * R;
+    int t = 0;
+    for (int r = r_begin; r < r_end; ++r) {
+#pragma unroll
+        for (int k = 0; k < R; ++k) rowmin[k] = kInf;
+        for (int cb = 0; cb < ncb; ++cb, ++t) {
+            const float* st = tile + (t & 1) * STAGE;
+            const int cnt = min(CDG_TILE, npad - cb * CDG_TILE);
+            int* col = mycol + cb * CDG_TILE;
+            mbar_wait(&bars[t & 1], (unsigned)((t >> 1) & 1));
+#pragma unroll 1
+            for (int j = 0; j < cnt; j += 4) {
+                const float4 X = *reinterpret_cast<const float4*>(st + j);
+                const float4 Y = *reinterpret_cast<const float4*>(st + CDG_TILE + j);
+                const float4 Z = *reinterpret_cast<const float4*>(st + 2 * CDG_TILE + j);
+                const float4 Q = *reinterpret_cast<const float4*>(st + 3 * CDG_TILE + j);
+                float c0, c1, c2, c3;
+                cdg_two_candidates<R>(ax, ay, az, aa, rowmin, X.x, Y.x, Z.x, Q.x, X.y, Y.y, Z.y, Q.y, c0, c1);
+                const int k0 = __reduce_min_sync(kFull, cdg_key(c0));
+                const int k1 = __reduce_min_sync(kFull, cdg_key(c1));
+                cdg_two_candidates<R>(ax, ay, az, aa, rowmin, X.z, Y.z, Z.z, Q.z, X.w, Y.w, Z.w, Q.w, c2, c3);
+                const int k2 = __reduce_min_sync(kFull, cdg_key(c2));
+                const int k3 = __reduce_min_sync(kFull, cdg_key(c3));
+                // this warp meets each candidate exactly once per cloud pair: its column minimum is final, plain store
+                if (lane == 0) *reinterpret_cast<int4*>(col + j) = make_int4(k0, k1, k2, k3);
+            }
+            __syncthreads();  // stage drained by every warp
+            if (tid == 0 && t + 2 < ntiles) {
+                fence_proxy_async();
+                issue(t + 2);
+            }
+        }
+        float total = 0.f;
+#pragma unroll
+        for (int k = 0; k < R; ++k)
+            if (k < nvalid) total += rowmin[k];
+        // fold this half's column minima: min over its 4 warps of e, plus |b_j|^2
+        const float* bb = PB + ((size_t)r * 4 + 3) * npad;
+        for (int j = ht; j < npts; j += CD_HALF) {
+            const int key = min(min(halfcol[j], halfcol[npad + j]), min(halfcol[2 * npad + j], halfcol[3 * npad + j]));
+            total += __fadd_rn(__int_as_float(key ^ ((key >> 31) & 0x7fffffff)), __ldg(bb + j));
+        }
+        total = warp_sum(total);
+        if (lane == 0) red[half * 4 + hw] = total;
+        __syncthreads();
+        if (ht == 0 && s_valid) {
+            const float* rr = red + half * 4;
+            // a cloud against itself is exactly 0 (the Gram form would leave rounding noise on the diagonal)
+            out[(size_t)s * ld_out + r] = (SYM && s == r) ? 0.f : (rr[0] + rr[1] + rr[2] + rr[3]) * inv_n;
+        }
+    }
+}
+
+template <int NH>
+constexpr size_t cdg_smem_bytes(int npad) {
+    return (size_t)(2 * 4 * CDG_TILE + NH * 4 * (size_t)npad + NH * 4) * 4 + 2 * sizeof(uint64_t);
 }
 
 // out[r][s] = out[s][r] for r > s (square matrix)

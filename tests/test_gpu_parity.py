@@ -241,7 +241,9 @@ def test_cd_allpairs_vs_oracle(dev, na, nb, npts, maker):
     A, B = maker(rng, na, npts, 3), maker(rng, nb, npts, 3)
     out = C(ops.cd_allpairs(G(A, dev), G(B, dev)))
     ref = ocpu.cd_allpairs(A, B)
-    np.testing.assert_allclose(out, ref, rtol=2e-6, atol=1e-9)
+    # centred clouds of <= 2048 points take the Gram-form kernel (the reference's own arithmetic, 1e-5 contract); larger clouds
+    # and the PDGN_B200_CD_EXACT=1 / off-centre cases below the direct form (2e-6 of the oracle)
+    np.testing.assert_allclose(out, ref, rtol=(3e-6 if npts > 2048 else 1e-5), atol=1e-9)
 
 
 def test_cd_allpairs_tiles_and_host_path(dev):
@@ -252,7 +254,7 @@ def test_cd_allpairs_tiles_and_host_path(dev):
     ref = ocpu.cd_allpairs(A, B)
     dA, dB = G(A, dev), G(B, dev)
     full = C(ops.cd_allpairs(dA, dB))
-    np.testing.assert_allclose(full, ref, rtol=2e-6)
+    np.testing.assert_allclose(full, ref, rtol=1e-5)
     for rows, cols in [((0, 9), (0, 11)), ((2, 7), (3, 4)), ((8, 9), (0, 11)), ((0, 5), (10, 11))]:
         tile = C(ops.cd_allpairs(dA, dB, rows=rows, cols=cols))
         np.testing.assert_array_equal(tile, full[rows[0]:rows[1], cols[0]:cols[1]])
@@ -272,8 +274,8 @@ def test_cd_allpairs_same_set_uses_symmetry(dev, n, npts):
     dA = G(A, dev)
     sym = C(ops.cd_allpairs(dA, dA))
     full = C(ops.cd_allpairs(dA, dA.clone()))  # different pointer => general path
-    np.testing.assert_allclose(sym, ocpu.cd_allpairs(A, A), rtol=2e-6, atol=1e-9)
-    np.testing.assert_allclose(sym, full, rtol=2e-6, atol=1e-9)
+    np.testing.assert_allclose(sym, ocpu.cd_allpairs(A, A), rtol=1e-5, atol=1e-7)
+    np.testing.assert_allclose(sym, full, rtol=1e-5, atol=1e-7)   # (the general path leaves Gram rounding noise on its diagonal)
     assert np.array_equal(sym, sym.T) and np.all(np.diag(sym) == 0)
 
 
@@ -309,14 +311,14 @@ def test_cd_allpairs_full_size_properties(dev):
     dA, dB = G(A, dev), G(B, dev)
     M = C(ops.cd_allpairs(dA, dB))
     Mt = C(ops.cd_allpairs(dB, dA))
-    np.testing.assert_allclose(M, Mt.T, rtol=2e-6)
+    np.testing.assert_allclose(M, Mt.T, rtol=1e-5)
     Maa = C(ops.cd_allpairs(dA, dA))
     assert np.all(np.diag(Maa) == 0)
     np.testing.assert_allclose(Maa, Maa.T, rtol=2e-6)
     pick = np.random.default_rng(2).integers(0, 80, size=(12, 2))
     for s, r in pick:
         ref = ocpu.cd_allpairs(A[s:s + 1], B[r:r + 1])[0, 0]
-        assert abs(M[s, r] - ref) <= 2e-6 * ref
+        assert abs(M[s, r] - ref) <= 1e-5 * ref
 
 
 # ------------------------------------------------------------------------------------------------ approximate EMD
@@ -839,3 +841,57 @@ def test_get_local_pair_answers_from_the_noted_generator_outputs(dev):
     local_pair.note_generator_outputs(tuple(ys))
     assert local_pair._noted_pair(ys[1], ys[0], 20) is None
     local_pair.note_generator_outputs(())
+
+
+# ------------------------------------------------------------------------------------------------ Gram-form / direct-form CD
+def test_cd_allpairs_gram_gate_and_exact_switch(dev):
+    """The all-pairs kernel has two arithmetic forms.  Centred clouds (every normalised shape set) take the Gram form
+    |a|^2 + |b|^2 - 2a.b -- the reference's own default arithmetic (evaluation_metrics.py:35-45), 1e-5 contract.  Clouds that are
+    NOT centred where their points lie (far from the origin, scattered positions, non-finite coordinates) are gated, on the
+    device, to the direct form whose minima are bit-identical to NmDistanceKernel; PDGN_B200_CD_EXACT=1 forces it everywhere."""
+    import os
+    import subprocess
+    import sys
+    from oracle import cpu as ocpu
+    from pdgn_b200 import ops
+    rng = np.random.default_rng(61)
+    A, B = clouds_sphere(rng, 6, 1024, 3), clouds_sphere(rng, 5, 1024, 3)
+    ref = ocpu.cd_allpairs(A, B)
+    gram = C(ops.cd_allpairs(G(A, dev), G(B, dev)))
+    np.testing.assert_allclose(gram, ref, rtol=1e-5)
+    assert np.abs(gram / ref - 1).max() < 5e-6                      # typical error is ~1e-6: the tolerance has slack
+    # off-centre: the same clouds 40 units away -> gate -> direct form: 2e-6 of the oracle although |p|^2 ~ 1600
+    off = np.array([40.0, -25.0, 10.0], np.float32)
+    Ao, Bo = (A + off).astype(np.float32), (B + off).astype(np.float32)
+    np.testing.assert_allclose(C(ops.cd_allpairs(G(Ao, dev), G(Bo, dev))), ocpu.cd_allpairs(Ao, Bo), rtol=2e-6)
+    # scattered clouds (each at its own position): direct form too
+    As = (A + rng.uniform(-20, 20, (6, 1, 3))).astype(np.float32)
+    np.testing.assert_allclose(C(ops.cd_allpairs(G(As, dev), G(B, dev))), ocpu.cd_allpairs(As, B), rtol=2e-6)
+    # near-planar set with tiny neighbour distances (predicted Gram error 9e-6 > 3e-6): direct form
+    Ap = rng.uniform(-1, 1, (4, 2048, 3)).astype(np.float32)
+    Ap[..., 2] *= 1e-3
+    np.testing.assert_allclose(C(ops.cd_allpairs(G(Ap, dev), G(Ap[::-1].copy(), dev))), ocpu.cd_allpairs(Ap, Ap[::-1].copy()), rtol=2e-6, atol=1e-12)
+    # a NaN coordinate anywhere: direct form (whose NaN behaviour is the reference kernel's)
+    An = A.copy()
+    An[2, 7, 1] = np.nan
+    out_n = C(ops.cd_allpairs(G(An, dev), G(B, dev)))
+    np.testing.assert_allclose(np.delete(out_n, 2, axis=0), np.delete(ref, 2, axis=0), rtol=2e-6)
+    code = r"""
+import sys
+import numpy as np, torch
+sys.path.insert(0, %r); sys.path.insert(0, %r)
+from conftest import clouds_sphere, clouds_uniform
+from oracle import cpu as ocpu
+from pdgn_b200 import ops
+rng = np.random.default_rng(62)
+for maker, na, nb, npts in [(clouds_sphere, 5, 3, 2048), (clouds_uniform, 3, 4, 100), (clouds_sphere, 6, 5, 128)]:
+    A, B = maker(rng, na, npts, 3), maker(rng, nb, npts, 3)
+    out = ops.cd_allpairs(torch.from_numpy(A).cuda(), torch.from_numpy(B).cuda()).cpu().numpy()
+    np.testing.assert_allclose(out, ocpu.cd_allpairs(A, B), rtol=2e-6, atol=1e-9)
+dA = torch.from_numpy(clouds_sphere(rng, 9, 256, 3)).cuda()
+sym = ops.cd_allpairs(dA, dA)
+assert torch.equal(sym, sym.t()) and bool((sym.diagonal() == 0).all())
+print('exact ok')
+""" % (os.path.dirname(os.path.dirname(os.path.abspath(__file__))), os.path.dirname(os.path.abspath(__file__)))
+    r = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, timeout=600, env=dict(os.environ, PDGN_B200_CD_EXACT="1"))
+    assert r.returncode == 0 and "exact ok" in r.stdout, r.stdout[-2000:] + r.stderr[-3000:]

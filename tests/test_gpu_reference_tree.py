@@ -384,7 +384,7 @@ def test_compute_all_metrics_with_emd_vs_reference_over_reference_kernels(dev, r
     from pdgn_b200 import evaluation_metrics as em      # `import *` does not bind the underscore name (nor does the reference's)
     cd_g, emd_g = em._pairwise_EMD_CD_(smp, rf, 32)
     torch.testing.assert_close(cd_g, cd_w, rtol=1e-5, atol=0)
-    torch.testing.assert_close(cd_g[:8], cd_a, rtol=2e-6, atol=0)
+    torch.testing.assert_close(cd_g[:8], cd_a, rtol=1e-5, atol=0)     # its direct-form kernel (ours: Gram form on centred clouds)
     # approximate EMD: 9 annealing levels with clamped feedback amplify the ex2.approx / shared-exponential rounding differences
     # (DESIGN.md 4.5); worst of 4096 pairs seen 3.1e-4, typical 3e-6 -- far below the auction's own approximation error, and the
     # argmin-based metrics above are identical
