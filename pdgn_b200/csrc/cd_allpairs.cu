@@ -48,17 +48,32 @@ static int cd_launch(bool sym, dim3 grid, size_t smem, cudaStream_t st, const fl
     return PDGN_OK;
 }
 
-static int cdg_launch(bool sym, dim3 grid, size_t smem, cudaStream_t st, const float* PA, const float* PB, int nrows, int ncols,
-                      int npts, int npad, int rstrip, float* out, long long ld_out, const unsigned* gate) {
+template <int OPT>
+static int cdg_launch_opt(bool sym, dim3 grid, size_t smem, cudaStream_t st, const float* PA, const float* PB, int nrows, int ncols,
+                          int npts, int npad, int rstrip, float* out, long long ld_out, const unsigned* gate) {
     if (sym) {
-        PDGN_CUDA(cudaFuncSetAttribute(cd_gram_kernel<CD_R, CD_NH, CD_MINB, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        cd_gram_kernel<CD_R, CD_NH, CD_MINB, true><<<grid, CD_THREADS, smem, st>>>(PA, PB, nrows, ncols, npts, npad, rstrip, out, ld_out, gate);
+        PDGN_CUDA(cudaFuncSetAttribute(cd_gram_kernel<CD_R, CD_NH, CD_MINB, true, OPT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        cd_gram_kernel<CD_R, CD_NH, CD_MINB, true, OPT><<<grid, CD_THREADS, smem, st>>>(PA, PB, nrows, ncols, npts, npad, rstrip, out, ld_out, gate);
     } else {
-        PDGN_CUDA(cudaFuncSetAttribute(cd_gram_kernel<CD_R, CD_NH, CD_MINB, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        cd_gram_kernel<CD_R, CD_NH, CD_MINB, false><<<grid, CD_THREADS, smem, st>>>(PA, PB, nrows, ncols, npts, npad, rstrip, out, ld_out, gate);
+        PDGN_CUDA(cudaFuncSetAttribute(cd_gram_kernel<CD_R, CD_NH, CD_MINB, false, OPT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        cd_gram_kernel<CD_R, CD_NH, CD_MINB, false, OPT><<<grid, CD_THREADS, smem, st>>>(PA, PB, nrows, ncols, npts, npad, rstrip, out, ld_out, gate);
     }
     PDGN_CHECK_LAUNCH();
     return PDGN_OK;
+}
+
+constexpr int CDG_OPT = 0;   // shipped inner-loop form (bit 0: unroll 2, bit 1: software-pipelined loads; profiles/r02_cd_gram_tune.txt)
+
+static int cdg_launch(bool sym, dim3 grid, size_t smem, cudaStream_t st, const float* PA, const float* PB, int nrows, int ncols,
+                      int npts, int npad, int rstrip, float* out, long long ld_out, const unsigned* gate) {
+    static const char* opt = tune_env("PDGN_CDG_OPT");   // tuning hook
+    const int o = opt ? atoi(opt) : CDG_OPT;
+    switch (o) {
+        case 1: return cdg_launch_opt<1>(sym, grid, smem, st, PA, PB, nrows, ncols, npts, npad, rstrip, out, ld_out, gate);
+        case 2: return cdg_launch_opt<2>(sym, grid, smem, st, PA, PB, nrows, ncols, npts, npad, rstrip, out, ld_out, gate);
+        case 3: return cdg_launch_opt<3>(sym, grid, smem, st, PA, PB, nrows, ncols, npts, npad, rstrip, out, ld_out, gate);
+        default: return cdg_launch_opt<0>(sym, grid, smem, st, PA, PB, nrows, ncols, npts, npad, rstrip, out, ld_out, gate);
+    }
 }
 
 // PDGN_B200_CD_EXACT=1 (a product switch, read once): every tile uses the direct-form kernel, whose minima are bit-identical to

@@ -392,7 +392,7 @@ __device__ __forceinline__ void cdg_two_candidates(const float (&ax)[R], const f
 
 // Same CTA shape as cd_allpairs_kernel (NH halves of 128 threads, R rows per thread, one row block: npts <= R*128), per-warp
 // column arrays (plain STS.128 of four CREDUX results, no atomics).  PA / PB: [cloud][4][npad] from cd_pack_gram_kernel.
-template <int R, int NH, int MINB, bool SYM>
+template <int R, int NH, int MINB, bool SYM, int OPT = 0>
 __global__ void __launch_bounds__(NH * CD_HALF, MINB)
 cd_gram_kernel(const float* __restrict__ PA, const float* __restrict__ PB, int nrows, int ncols, int npts, int npad, int rstrip,
                float* __restrict__ out, long long ld_out, const unsigned* __restrict__ gate) {
@@ -464,12 +464,7 @@ cd_gram_kernel(const float* __restrict__ PA, const float* __restrict__ PB, int n
             const int cnt = min(CDG_TILE, npad - cb * CDG_TILE);
             int* col = mycol + cb * CDG_TILE;
             mbar_wait(&bars[t & 1], (unsigned)((t >> 1) & 1));
-#pragma unroll 1
-            for (int j = 0; j < cnt; j += 4) {
-                const float4 X = *reinterpret_cast<const float4*>(st + j);
-                const float4 Y = *reinterpret_cast<const float4*>(st + CDG_TILE + j);
-                const float4 Z = *reinterpret_cast<const float4*>(st + 2 * CDG_TILE + j);
-                const float4 Q = *reinterpret_cast<const float4*>(st + 3 * CDG_TILE + j);
+            auto quad = [&](const float4& X, const float4& Y, const float4& Z, const float4& Q, int j) {
                 float c0, c1, c2, c3;
                 cdg_two_candidates<R>(ax, ay, az, aa, rowmin, X.x, Y.x, Z.x, Q.x, X.y, Y.y, Z.y, Q.y, c0, c1);
                 const int k0 = __reduce_min_sync(kFull, cdg_key(c0));
@@ -479,6 +474,27 @@ cd_gram_kernel(const float* __restrict__ PA, const float* __restrict__ PB, int n
                 const int k3 = __reduce_min_sync(kFull, cdg_key(c3));
                 // this warp meets each candidate exactly once per cloud pair: its column minimum is final, plain store
                 if (lane == 0) *reinterpret_cast<int4*>(col + j) = make_int4(k0, k1, k2, k3);
+            };
+            if (OPT & 2) {  // software-pipelined loads: the next quad is in flight while this one is consumed
+                float4 X = *reinterpret_cast<const float4*>(st), Y = *reinterpret_cast<const float4*>(st + CDG_TILE);
+                float4 Z = *reinterpret_cast<const float4*>(st + 2 * CDG_TILE), Q = *reinterpret_cast<const float4*>(st + 3 * CDG_TILE);
+#pragma unroll((OPT & 1) ? 2 : 1)
+                for (int j = 0; j < cnt; j += 4) {
+                    const int jn = (j + 4 < cnt) ? j + 4 : j;
+                    const float4 Xn = *reinterpret_cast<const float4*>(st + jn), Yn = *reinterpret_cast<const float4*>(st + CDG_TILE + jn);
+                    const float4 Zn = *reinterpret_cast<const float4*>(st + 2 * CDG_TILE + jn), Qn = *reinterpret_cast<const float4*>(st + 3 * CDG_TILE + jn);
+                    quad(X, Y, Z, Q, j);
+                    X = Xn; Y = Yn; Z = Zn; Q = Qn;
+                }
+            } else {
+#pragma unroll((OPT & 1) ? 2 : 1)
+                for (int j = 0; j < cnt; j += 4) {
+                    const float4 X = *reinterpret_cast<const float4*>(st + j);
+                    const float4 Y = *reinterpret_cast<const float4*>(st + CDG_TILE + j);
+                    const float4 Z = *reinterpret_cast<const float4*>(st + 2 * CDG_TILE + j);
+                    const float4 Q = *reinterpret_cast<const float4*>(st + 3 * CDG_TILE + j);
+                    quad(X, Y, Z, Q, j);
+                }
             }
             __syncthreads();  // stage drained by every warp
             if (tid == 0 && t + 2 < ntiles) {
