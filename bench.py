@@ -221,10 +221,19 @@ def main():
     torch.cuda.set_device(local_rank)
     dev = torch.device("cuda", local_rank)
     if world > 1:
-        # keep stdout to the one JSON line: NCCL writes its debug output (the version banner at WARN and above) to stdout
-        # unless told otherwise
-        os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
-        dist.init_process_group("nccl", device_id=dev)
+        # keep stdout to the one JSON line: NCCL prints its version banner (and any NCCL_DEBUG output) on stdout while the
+        # communicator is created, so file descriptor 1 points at stderr until the first collective has completed
+        sys.stdout.flush()
+        saved_fd = os.dup(1)
+        os.dup2(2, 1)
+        try:
+            dist.init_process_group("nccl", device_id=dev)
+            dist.barrier()
+            torch.cuda.synchronize()
+        finally:
+            sys.stdout.flush()
+            os.dup2(saved_fd, 1)
+            os.close(saved_fd)
     from pdgn_b200 import _build
     if rank == 0:
         _build.build()

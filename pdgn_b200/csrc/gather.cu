@@ -212,6 +212,9 @@ __device__ __forceinline__ void pull_list(const int* __restrict__ pb, int a, int
     }
 }
 
+#ifndef PDGN_PULL_ECACHE
+#define PDGN_PULL_ECACHE 16
+#endif
 constexpr int PULL_LONG = 64;  // lists longer than this are summed by a whole warp
 constexpr int PULL_CC = 4;     // channel rows staged per CTA (upper bound)
 
@@ -310,7 +313,7 @@ __global__ void __launch_bounds__(1024, 1) pull_stream_kernel(const float* __res
                                                           int chunks_per_cta, float* __restrict__ dst,
                                                           const float* __restrict__ wgt) {
     constexpr int NR = MODE == 1 ? 2 * CC : CC;    // rows staged per chunk (MODE 1: CC g0 rows, then CC g1 rows)
-    constexpr int ECACHE = 16;                     // list entries cached in registers across the chunks
+    constexpr int ECACHE = PDGN_PULL_ECACHE;       // list entries cached in registers across the chunks
     extern __shared__ __align__(128) float buf[];  // [2][NR*rowlen]
     __shared__ uint64_t bars[2];
     __shared__ int nlong, longlist[512];
