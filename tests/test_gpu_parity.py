@@ -895,3 +895,25 @@ print('exact ok')
 """ % (os.path.dirname(os.path.dirname(os.path.abspath(__file__))), os.path.dirname(os.path.abspath(__file__)))
     r = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, timeout=600, env=dict(os.environ, PDGN_B200_CD_EXACT="1"))
     assert r.returncode == 0 and "exact ok" in r.stdout, r.stdout[-2000:] + r.stderr[-3000:]
+
+
+def test_cd_allpairs_headline_size_sampled_against_oracle(dev):
+    """The bench workload itself (1000 x 1000 clouds x 2048 points, seeds 0 / 1 as bench.make_clouds builds them): 24 sampled
+    entries of the full matrix against the CPU oracle (1e-5 contract), every entry finite and positive, and the full matrix
+    equal to its 2-D tiles (what the ranks of a multi-GPU run compute)."""
+    import bench
+    from oracle import cpu as ocpu
+    from pdgn_b200 import dist as pd
+    from pdgn_b200 import ops
+    A, B = bench.make_clouds(0), bench.make_clouds(1)
+    dA, dB = A.to(dev), B.to(dev)
+    M = ops.cd_allpairs(dA, dB)
+    assert tuple(M.shape) == (1000, 1000) and bool(torch.isfinite(M).all()) and bool((M > 0).all())
+    Mh = C(M)
+    pick = np.random.default_rng(3).integers(0, 1000, size=(24, 2))
+    for s, r in pick:
+        ref = ocpu.cd_allpairs(A[s:s + 1].numpy(), B[r:r + 1].numpy())[0, 0]
+        assert abs(Mh[s, r] - ref) <= 1e-5 * ref, (s, r, Mh[s, r], ref)
+    for rank in (0, 5):
+        rows, cols = pd.tile_of(rank, 8, 1000, 1000)
+        assert torch.equal(ops.cd_allpairs(dA, dB, rows=rows, cols=cols), M[rows[0]:rows[1], cols[0]:cols[1]])
