@@ -72,6 +72,9 @@ static int cdg_launch(bool sym, dim3 grid, size_t smem, cudaStream_t st, const f
         case 1: return cdg_launch_opt<1>(sym, grid, smem, st, PA, PB, nrows, ncols, npts, npad, rstrip, out, ld_out, gate);
         case 2: return cdg_launch_opt<2>(sym, grid, smem, st, PA, PB, nrows, ncols, npts, npad, rstrip, out, ld_out, gate);
         case 3: return cdg_launch_opt<3>(sym, grid, smem, st, PA, PB, nrows, ncols, npts, npad, rstrip, out, ld_out, gate);
+        case 4: return cdg_launch_opt<4>(sym, grid, smem, st, PA, PB, nrows, ncols, npts, npad, rstrip, out, ld_out, gate);
+        case 8: return cdg_launch_opt<8>(sym, grid, smem, st, PA, PB, nrows, ncols, npts, npad, rstrip, out, ld_out, gate);
+        case 12: return cdg_launch_opt<12>(sym, grid, smem, st, PA, PB, nrows, ncols, npts, npad, rstrip, out, ld_out, gate);
         default: return cdg_launch_opt<0>(sym, grid, smem, st, PA, PB, nrows, ncols, npts, npad, rstrip, out, ld_out, gate);
     }
 }

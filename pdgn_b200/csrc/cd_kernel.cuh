@@ -370,13 +370,15 @@ __device__ __forceinline__ int cdg_key(float v) {  // order-preserving float -> 
     return b ^ ((b >> 31) & 0x7fffffff);
 }
 
-// Two candidates against the thread's R rows (Gram form): row minima on e + bb, column partial minima on e.
-template <int R>
+// Two candidates against the thread's R rows (Gram form): row minima on e + bb, column partial minima on e.  SPLIT: two
+// independent column chains per candidate (rows 0..R/2-1 and R/2..R-1) merged at the end -- half the dependent-FMNMX3 depth.
+template <int R, bool SPLIT = false>
 __device__ __forceinline__ void cdg_two_candidates(const float (&ax)[R], const float (&ay)[R], const float (&az)[R], const float (&aa)[R],
                                                    float (&rowmin)[R], float x0, float y0, float z0, float b0, float x1, float y1,
                                                    float z1, float b1, float& c0, float& c1) {
     c0 = kInf;
     c1 = kInf;
+    float d0 = kInf, d1 = kInf;
 #pragma unroll
     for (int k = 0; k < R; k += 2) {
         const float e00 = __fmaf_rn(ax[k], x0, __fmaf_rn(ay[k], y0, __fmaf_rn(az[k], z0, aa[k])));
@@ -385,8 +387,17 @@ __device__ __forceinline__ void cdg_two_candidates(const float (&ax)[R], const f
         const float e11 = __fmaf_rn(ax[k + 1], x1, __fmaf_rn(ay[k + 1], y1, __fmaf_rn(az[k + 1], z1, aa[k + 1])));
         rowmin[k] = min3(rowmin[k], __fadd_rn(e00, b0), __fadd_rn(e01, b1));
         rowmin[k + 1] = min3(rowmin[k + 1], __fadd_rn(e10, b0), __fadd_rn(e11, b1));
-        c0 = min3(c0, e00, e10);
-        c1 = min3(c1, e01, e11);
+        if (SPLIT && k >= R / 2) {
+            d0 = min3(d0, e00, e10);
+            d1 = min3(d1, e01, e11);
+        } else {
+            c0 = min3(c0, e00, e10);
+            c1 = min3(c1, e01, e11);
+        }
+    }
+    if (SPLIT) {
+        c0 = fminf(c0, d0);
+        c1 = fminf(c1, d1);
     }
 }
 
@@ -466,15 +477,39 @@ cd_gram_kernel(const float* __restrict__ PA, const float* __restrict__ PB, int n
             mbar_wait(&bars[t & 1], (unsigned)((t >> 1) & 1));
             auto quad = [&](const float4& X, const float4& Y, const float4& Z, const float4& Q, int j) {
                 float c0, c1, c2, c3;
-                cdg_two_candidates<R>(ax, ay, az, aa, rowmin, X.x, Y.x, Z.x, Q.x, X.y, Y.y, Z.y, Q.y, c0, c1);
+                cdg_two_candidates<R, (OPT & 4) != 0>(ax, ay, az, aa, rowmin, X.x, Y.x, Z.x, Q.x, X.y, Y.y, Z.y, Q.y, c0, c1);
                 const int k0 = __reduce_min_sync(kFull, cdg_key(c0));
                 const int k1 = __reduce_min_sync(kFull, cdg_key(c1));
-                cdg_two_candidates<R>(ax, ay, az, aa, rowmin, X.z, Y.z, Z.z, Q.z, X.w, Y.w, Z.w, Q.w, c2, c3);
+                cdg_two_candidates<R, (OPT & 4) != 0>(ax, ay, az, aa, rowmin, X.z, Y.z, Z.z, Q.z, X.w, Y.w, Z.w, Q.w, c2, c3);
                 const int k2 = __reduce_min_sync(kFull, cdg_key(c2));
                 const int k3 = __reduce_min_sync(kFull, cdg_key(c3));
                 // this warp meets each candidate exactly once per cloud pair: its column minimum is final, plain store
                 if (lane == 0) *reinterpret_cast<int4*>(col + j) = make_int4(k0, k1, k2, k3);
             };
+            if (OPT & 8) {
+                // deferred epilogue: the column partial minima of quad j are reduced across the warp (CREDUX) and stored while
+                // the FFMAs of quad j+1 issue, instead of in an ALU-only burst at the end of the body
+                float p0 = kInf, p1 = kInf, p2 = kInf, p3 = kInf;
+#pragma unroll 1
+                for (int j = 0; j < cnt; j += 4) {
+                    const float4 X = *reinterpret_cast<const float4*>(st + j);
+                    const float4 Y = *reinterpret_cast<const float4*>(st + CDG_TILE + j);
+                    const float4 Z = *reinterpret_cast<const float4*>(st + 2 * CDG_TILE + j);
+                    const float4 Q = *reinterpret_cast<const float4*>(st + 3 * CDG_TILE + j);
+                    float c0, c1, c2, c3;
+                    cdg_two_candidates<R, (OPT & 4) != 0>(ax, ay, az, aa, rowmin, X.x, Y.x, Z.x, Q.x, X.y, Y.y, Z.y, Q.y, c0, c1);
+                    if (j > 0) {
+                        const int k0 = __reduce_min_sync(kFull, cdg_key(p0)), k1 = __reduce_min_sync(kFull, cdg_key(p1));
+                        const int k2 = __reduce_min_sync(kFull, cdg_key(p2)), k3 = __reduce_min_sync(kFull, cdg_key(p3));
+                        if (lane == 0) *reinterpret_cast<int4*>(col + j - 4) = make_int4(k0, k1, k2, k3);
+                    }
+                    cdg_two_candidates<R, (OPT & 4) != 0>(ax, ay, az, aa, rowmin, X.z, Y.z, Z.z, Q.z, X.w, Y.w, Z.w, Q.w, c2, c3);
+                    p0 = c0; p1 = c1; p2 = c2; p3 = c3;
+                }
+                const int k0 = __reduce_min_sync(kFull, cdg_key(p0)), k1 = __reduce_min_sync(kFull, cdg_key(p1));
+                const int k2 = __reduce_min_sync(kFull, cdg_key(p2)), k3 = __reduce_min_sync(kFull, cdg_key(p3));
+                if (lane == 0) *reinterpret_cast<int4*>(col + cnt - 4) = make_int4(k0, k1, k2, k3);
+            } else
             if (OPT & 2) {  // software-pipelined loads: the next quad is in flight while this one is consumed
                 float4 X = *reinterpret_cast<const float4*>(st), Y = *reinterpret_cast<const float4*>(st + CDG_TILE);
                 float4 Z = *reinterpret_cast<const float4*>(st + 2 * CDG_TILE), Q = *reinterpret_cast<const float4*>(st + 3 * CDG_TILE);
