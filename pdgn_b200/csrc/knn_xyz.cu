@@ -21,7 +21,7 @@
 //           many survivors precede its own in (d2, index) order and, if that rank is < k, stores straight into
 //           idx[rank].  Warp-uniform control flow throughout.
 //   A survivor overflow (adversarial ties / clustering / fewer than k finite candidates) sends that one query to
-//   an exact serial scan, so the result is always exact.
+//   a warp-cooperative exact selection (k rounds of a min-search over all candidates), so the result is always exact.
 // Generic path (knn_generic_kernel): any k <= 128, any n; threshold-guarded insertion into a shared-memory list.
 #include <cstdlib>
 #include "common.cuh"
@@ -442,26 +442,36 @@ __device__ __forceinline__ void knn_select_body(const float* __restrict__ xyz, c
                 oi[e] = 0;
                 if (od) od[e] = kInf;
             }
-        } else if (lane == 0) {
-            // survivor overflow: exact serial scan of every candidate for this query (the key array doubles as the list)
-            float* ldl = reinterpret_cast<float*>(sel.key);
-            int* lil = reinterpret_cast<int*>(sel.key) + KS_SCAP;
+        } else {
+            // survivor overflow (duplicates, clusters, fewer than k finite candidates): warp-cooperative exact selection.  k rounds of
+            // "smallest (d2, index) key above the previous winner"; every lane scans n/32 candidates per round, one min-reduction
+            // per round.  Exact by construction, ~k*n/32 distance evaluations per lane instead of n serial ones on lane 0.
+            unsigned long long last = 0;
             for (int e = 0; e < k; ++e) {
-                ldl[e] = kInf;
-                lil[e] = 0;
-            }
-            float thr = kInf;
-            for (int j = 0; j < n; ++j) {
-                const float* c = pb + (size_t)j * 3;
-                const float d = d2_xyz(ax, ay, az, __ldg(c), __ldg(c + 1), __ldg(c + 2));
-                if (d < thr) {
-                    list_insert(ldl, lil, 1, 0, k, d, j);
-                    thr = ldl[k - 1];
+                unsigned long long best = ~0ull;
+                for (int j = lane; j < n; j += 32) {
+                    const float* c = pb + (size_t)j * 3;
+                    const float d = d2_xyz(ax, ay, az, __ldg(c), __ldg(c + 1), __ldg(c + 2));
+                    const unsigned long long key = ((unsigned long long)__float_as_uint(d) << 32) | (unsigned)j;
+                    if (d <= 3.402823466e+38f && (e == 0 || key > last) && key < best) best = key;   // NaN / +inf never selected
                 }
-            }
-            for (int e = 0; e < k; ++e) {
-                oi[e] = lil[e];
-                if (od) od[e] = ldl[e];
+#pragma unroll
+                for (int o = 16; o > 0; o >>= 1) {
+                    const unsigned long long other = __shfl_xor_sync(kFull, best, o);
+                    best = other < best ? other : best;
+                }
+                if (best == ~0ull) {
+                    for (int f = e + lane; f < k; f += 32) {
+                        oi[f] = 0;
+                        if (od) od[f] = kInf;
+                    }
+                    break;
+                }
+                if (lane == 0) {
+                    oi[e] = (int)(unsigned)best;
+                    if (od) od[e] = __uint_as_float((unsigned)(best >> 32));
+                }
+                last = best;
             }
         }
         __syncwarp();

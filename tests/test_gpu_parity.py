@@ -917,3 +917,46 @@ def test_cd_allpairs_headline_size_sampled_against_oracle(dev):
     for rank in (0, 5):
         rows, cols = pd.tile_of(rank, 8, 1000, 1000)
         assert torch.equal(ops.cd_allpairs(dA, dB, rows=rows, cols=cols), M[rows[0]:rows[1], cols[0]:cols[1]])
+
+
+def test_knn_duplicate_heavy_clouds_exact_and_bounded_time(dev):
+    """Heavily duplicated points (every point twice, one point n/8 times) overflow the survivor lists of BOTH kNN kernels: the
+    results must still be the oracle's (ties to the lower index), and the overflow path must stay a bounded slowdown (it is a
+    warp-cooperative exact selection, not a serial scan on one lane: ADVICE round 1)."""
+    import os
+    import subprocess
+    import sys
+    code = r"""
+import sys, time
+import numpy as np, torch
+sys.path.insert(0, %r); sys.path.insert(0, %r)
+from conftest import clouds_uniform
+from oracle import cpu as ocpu
+from pdgn_b200 import ops
+rng = np.random.default_rng(7)
+def dup(b, n):
+    v = clouds_uniform(rng, b, n, 3)
+    v[:, n // 2:] = v[:, : n - n // 2]
+    v[:, : n // 8] = v[:, :1]
+    return v
+for b, n, m in [(2, 2048, 300), (3, 1024, 1024), (2, 600, 77)]:
+    xyz = dup(b, n)
+    q = xyz[:, :m].copy()
+    idx, d2 = ops.knn_xyz(20, torch.from_numpy(xyz).cuda(), torch.from_numpy(q).cuda(), return_dist=True)
+    oi, od = ocpu.knn_xyz(xyz, q, 20)
+    assert np.array_equal(idx.cpu().numpy(), oi) and np.array_equal(d2.cpu().numpy(), od), (b, n, m)
+def ms(x):
+    ops.knn_xyz(20, x); torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record(); ops.knn_xyz(20, x); e1.record(); torch.cuda.synchronize()
+    return e0.elapsed_time(e1)
+clean = ms(torch.from_numpy(clouds_uniform(rng, 35, 2048, 3)).cuda())
+dirty = ms(torch.from_numpy(dup(35, 2048)).cuda())
+print('clean %%.3f ms, duplicate-heavy %%.3f ms' %% (clean, dirty))
+assert dirty < 60 * clean, (clean, dirty)
+print('dup ok')
+""" % (os.path.dirname(os.path.dirname(os.path.abspath(__file__))), os.path.dirname(os.path.abspath(__file__)))
+    for impl in ("gram", "select"):
+        env = dict(os.environ, PDGN_B200_TUNE="1", PDGN_KNN_IMPL=impl)
+        r = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, timeout=900, env=env)
+        assert r.returncode == 0 and "dup ok" in r.stdout, impl + "\n" + r.stdout[-2000:] + r.stderr[-3000:]
