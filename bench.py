@@ -491,6 +491,21 @@ def bench_gathers(dev, hbm_gbs, src):
     res["interp_c256"] = {"fwd_ms": f_ms, "fwd_gbs": nbytes / (f_ms * 1e-3) / 1e9, "fwd_frac": nbytes / (f_ms * 1e-3) / 1e9 / hbm_gbs,
                           "bwd_ms": b_ms, "bwd_gbs": nbytes / (b_ms * 1e-3) / 1e9, "bwd_frac": nbytes / (b_ms * 1e-3) / 1e9 / hbm_gbs,
                           "algorithmic_mb": nbytes / 1e6}
+    # edge features of the generator's last stage (get_edge_features, PDGNet_v2.py:461-477): C=256, N=1024, k=num_k//2=10.
+    # bytes = the [B,2C,N,k] tensor + x / grad_x + the int64 index
+    b, c, n, k = 35, 256, 1024, 10
+    x = torch.from_numpy(rng.standard_normal((b, c, n)).astype(np.float32)).to(dev)
+    idx64 = torch.from_numpy(rng.integers(0, n, (b, n, k)).astype(np.int64)).to(dev)
+    ee = torch.empty((b, 2 * c, n, k), dtype=torch.float32, device=dev)
+    gx = torch.zeros((b, c, n), dtype=torch.float32, device=dev)
+    ws_bytes = L.pdgn_edge_feat_bwd_workspace(b, n, k)
+    ws = torch.empty((ws_bytes,), dtype=torch.uint8, device=dev)
+    f_ms = _time_ms(lambda: L.pdgn_edge_feat_fwd(x.data_ptr(), idx64.data_ptr(), b, c, n, k, ee.data_ptr(), st), 10, flush)
+    b_ms = _time_ms(lambda: L.pdgn_edge_feat_bwd_ws(ee.data_ptr(), idx64.data_ptr(), b, c, n, k, gx.data_ptr(), ws.data_ptr(), ws_bytes, st), 10, flush)
+    nbytes = 4.0 * (2 * b * c * n * k + b * c * n) + 8.0 * b * n * k
+    res["edge_c256"] = {"fwd_ms": f_ms, "fwd_gbs": nbytes / (f_ms * 1e-3) / 1e9, "fwd_frac": nbytes / (f_ms * 1e-3) / 1e9 / hbm_gbs,
+                        "bwd_ms": b_ms, "bwd_gbs": nbytes / (b_ms * 1e-3) / 1e9, "bwd_frac": nbytes / (b_ms * 1e-3) / 1e9 / hbm_gbs,
+                        "algorithmic_mb": nbytes / 1e6}
     return res
 
 

@@ -12,6 +12,7 @@
 // re-reads it C times) and the random 4-byte gathers hit L1/L2-resident feature rows.
 #include <cstdlib>
 #include "common.cuh"
+#include "pull.cuh"
 
 namespace pdgn {
 
@@ -118,32 +119,70 @@ __global__ void __launch_bounds__(GT) group_fwd_smem_kernel(const float* __restr
 
 // Inverse index of idx[b] (values in [0,n), mk entries): offs[b][n+1], pos[b][mk] with every list in ascending
 // position order, so the pull kernels add each target's contributions in a fixed order (deterministic, unlike the
-// reference's float atomics).  The fill is a STABLE counting sort without atomics on the order: entries are taken in
-// tiles of blockDim.x consecutive positions; inside a warp __match_any_sync ranks equal targets by lane, and the warps
-// of a tile take their turn in order (one barrier per warp), so equal targets keep their position order regardless of
-// how skewed the index distribution is (feature-space kNN graphs have hubs with thousands of incoming edges).
+// reference's float atomics).  The fill is a STABLE counting sort with no block-wide barrier inside its loops: the entry
+// list is cut into one contiguous slice per warp and every warp keeps its OWN 16-bit counter row (cnt[w][target]); a column
+// prefix over the rows turns the counts into each warp's first slot inside a target's list, and the fill pass then only
+// needs warp-level ordering (__match_any_sync ranks equal targets by lane, the group leader advances the warp's cursor).
+// Equal targets keep their position order however skewed the index distribution is (feature-space kNN graphs have hubs
+// with thousands of incoming edges).  Round 1's version took the warps of a 1024-entry tile in turn (32 barriers per
+// tile): 25-38 us per call; this one is bounded by the three passes over idx.
 constexpr int CSR_T = 1024;
+
+__host__ __device__ inline int csr_warps(int n) {   // counter rows that fit ~200 KB (power of two, <= 32)
+    int w = 32;
+    while (w > 1 && (size_t)w * (size_t)((n + 1) & ~1) * 2 > 160 * 1024) w >>= 1;
+    return w;
+}
+static size_t csr_smem_bytes(int n) { return (size_t)csr_warps(n) * (size_t)((n + 1) & ~1) * 2 + (size_t)n * 4 + 32 * 4; }
+// shapes the kernel takes: counters of a (warp, target) pair are 16 bit, the counter block must fit shared memory
+static bool csr_ok(int n, long long mk) {
+    const int w = csr_warps(n);
+    const long long per = ((mk + w - 1) / w + 31) / 32 * 32;
+    return csr_smem_bytes(n) <= 200 * 1024 && per <= 65535 && mk <= 0x7fffffffLL;
+}
 
 template <typename IdxT>
 __global__ void __launch_bounds__(CSR_T) csr_build_kernel(const IdxT* __restrict__ idx, int n, int mk, int* __restrict__ offs,
                                                          int* __restrict__ pos) {
-    extern __shared__ int csr_sm[];  // cnt[n] | cursor[n] | warp sums[32]
-    int* cnt = csr_sm;
-    int* cursor = csr_sm + n;
-    int* wsum = cursor + n;
+    extern __shared__ __align__(16) unsigned char csr_raw[];
+    const int W = csr_warps(n), np = (n + 1) & ~1;
+    unsigned short* cnt = reinterpret_cast<unsigned short*>(csr_raw);                 // [W][np]
+    int* base = reinterpret_cast<int*>(csr_raw + (size_t)W * np * 2);               // [n] first slot of each target's list
+    int* wsum = base + n;                                                            // [32]
     const int bz = blockIdx.x, t = threadIdx.x, lane = t & 31, warp = t >> 5;
     const IdxT* ip = idx + (size_t)bz * mk;
     int* ob = offs + (size_t)bz * (n + 1);
     int* pb = pos + (size_t)bz * mk;
-    for (int p = t; p < n; p += CSR_T) cnt[p] = 0;
+    {
+        unsigned* z = reinterpret_cast<unsigned*>(cnt);
+        for (int i = t; i < W * np / 2; i += CSR_T) z[i] = 0u;
+    }
     __syncthreads();
-    for (int e = t; e < mk; e += CSR_T) atomicAdd(&cnt[(int)ip[e]], 1);  // integer counts: order irrelevant
+    // slice of warp w (w < W): entries [w * per, (w + 1) * per), per a multiple of 32
+    const int per = ((mk + W - 1) / W + 31) / 32 * 32;
+    const int e_lo = min(mk, warp * per), e_hi = warp < W ? min(mk, e_lo + per) : e_lo;
+    unsigned* cw = reinterpret_cast<unsigned*>(cnt + (size_t)(warp < W ? warp : 0) * np);
+    for (int e = e_lo + lane; e < e_hi; e += 32) {
+        const int tgt = (int)ip[e];
+        atomicAdd(&cw[tgt >> 1], 1u << ((tgt & 1) * 16));                           // integer counts: order irrelevant
+    }
     __syncthreads();
-    // exclusive scan: each thread owns a contiguous slice of targets
-    const int per = (n + CSR_T - 1) / CSR_T;
-    const int lo = min(n, t * per), hi = min(n, lo + per);
+    // column prefix: cnt[w][p] <- entries of target p in the slices before w; base[p] <- total for now
+    for (int p = t; p < n; p += CSR_T) {
+        int run = 0;
+        for (int w = 0; w < W; ++w) {
+            const int v = cnt[(size_t)w * np + p];
+            cnt[(size_t)w * np + p] = (unsigned short)run;
+            run += v;
+        }
+        base[p] = run;
+    }
+    __syncthreads();
+    // exclusive scan of the totals: each thread owns a contiguous slice of targets
+    const int tper = (n + CSR_T - 1) / CSR_T;
+    const int lo = min(n, t * tper), hi = min(n, lo + tper);
     int local = 0;
-    for (int p = lo; p < hi; ++p) local += cnt[p];
+    for (int p = lo; p < hi; ++p) local += base[p];
     int incl = local;
 #pragma unroll
     for (int o = 1; o < 32; o <<= 1) {
@@ -164,72 +203,31 @@ __global__ void __launch_bounds__(CSR_T) csr_build_kernel(const IdxT* __restrict
     __syncthreads();
     int run = incl - local + (warp ? wsum[warp - 1] : 0);
     for (int p = lo; p < hi; ++p) {
-        cursor[p] = run;
+        const int v = base[p];
+        base[p] = run;
         ob[p] = run;
-        run += cnt[p];
+        run += v;
     }
     if (t == CSR_T - 1) ob[n] = mk;
     __syncthreads();
+    // fill: the warp walks its slice in order, 32 entries at a time
     const unsigned lt = (1u << lane) - 1u;
-    for (int e0 = 0; e0 < mk; e0 += CSR_T) {
-        const int e = e0 + t;
-        const bool valid = e < mk;
-        const int tgt = valid ? (int)ip[e] : -1 - lane;               // invalid lanes match nobody
+    unsigned short* cur = cnt + (size_t)(warp < W ? warp : 0) * np;
+    for (int e0 = e_lo; e0 < e_hi; e0 += 32) {
+        const int e = e0 + lane;
+        const bool valid = e < e_hi;
+        const int tgt = valid ? (int)ip[e] : -1 - lane;                   // invalid lanes match nobody
         const unsigned peers = __match_any_sync(kFull, tgt);
         const int rank = __popc(peers & lt);
-        int base = 0;
-        for (int w = 0; w < CSR_T / 32; ++w) {
-            if (warp == w && valid && rank == 0) {                    // one leader per distinct target in this warp
-                base = cursor[tgt];
-                cursor[tgt] = base + __popc(peers);
-            }
-            __syncthreads();
+        int first = 0;
+        if (valid && rank == 0) {                                         // one leader per distinct target of the group
+            first = cur[tgt];
+            cur[tgt] = (unsigned short)(first + __popc(peers));
         }
-        base = __shfl_sync(kFull, base, __ffs(peers) - 1);
-        if (valid) pb[base + rank] = e;
+        first = __shfl_sync(kFull, first, __ffs(peers) - 1);
+        if (valid) pb[base[tgt] + first + rank] = e;
+        __syncwarp();
     }
-}
-
-// Multi-channel pull: acc[ch] += value(ch, e) for the entries pb[a..b) in list order (index loads four at a time,
-// every entry feeds all CC channel accumulators, so the list is read once per channel chunk).
-template <int CC, class F>
-__device__ __forceinline__ void pull_list(const int* __restrict__ pb, int a, int b, float (&acc)[CC], F value) {
-    int q = a;
-    for (; q + 4 <= b; q += 4) {
-        const int e0 = __ldg(pb + q), e1 = __ldg(pb + q + 1), e2 = __ldg(pb + q + 2), e3 = __ldg(pb + q + 3);
-#pragma unroll
-        for (int ch = 0; ch < CC; ++ch) {
-            acc[ch] += value(ch, e0);
-            acc[ch] += value(ch, e1);
-            acc[ch] += value(ch, e2);
-            acc[ch] += value(ch, e3);
-        }
-    }
-    for (; q < b; ++q) {
-        const int e = __ldg(pb + q);
-#pragma unroll
-        for (int ch = 0; ch < CC; ++ch) acc[ch] += value(ch, e);
-    }
-}
-
-#ifndef PDGN_PULL_ECACHE
-#define PDGN_PULL_ECACHE 24   // 16 / 24 / 32 entries: grouping bwd 169 / 165 / 175 us, edge-feature bwd 272 / 261 / 273 us at C=256
-#endif
-constexpr int PULL_LONG = 64;  // lists longer than this are summed by a whole warp
-constexpr int PULL_CC = 4;     // channel rows staged per CTA (upper bound)
-
-// Long list: lane l sums entries a+l, a+l+32, ... in order, then a fixed butterfly combines the 32 partial sums.
-template <int CC, class F>
-__device__ __forceinline__ void pull_list_warp(const int* __restrict__ pb, int a, int b, int lane, float (&acc)[CC], F value) {
-    for (int q = a + lane; q < b; q += 32) {
-        const int e = __ldg(pb + q);
-#pragma unroll
-        for (int ch = 0; ch < CC; ++ch) acc[ch] += value(ch, e);
-    }
-#pragma unroll
-    for (int ch = 0; ch < CC; ++ch)
-#pragma unroll
-        for (int o = 16; o > 0; o >>= 1) acc[ch] += __shfl_xor_sync(kFull, acc[ch], o);
 }
 
 // Shared skeleton of the three pull kernels.  `value(ch, e)` = contribution of entry e to channel ch (ch < cc is the
@@ -299,170 +297,6 @@ __global__ void __launch_bounds__(512) group_bwd_pull_kernel(const float* __rest
                  [&](int ch, int e) { return ch < cm ? rows[(size_t)ch * mk + e] : 0.f; },
                  [&](int, int) { return 0.f; },
                  [&](int ch, int p) { return dst + (size_t)ch * n + p; });
-}
-
-// Streaming pull (grouping and edge-feature backward, the two tensors that are hundreds of MB): one CTA walks several
-// channel chunks of one batch element; the CC rows of a chunk arrive by TMA bulk copy (cp.async.bulk + mbarrier) into
-// one of two shared buffers while the 1024 threads pull the previous chunk, so HBM streams continuously and the
-// latency of the list walk hides under it.  MODE 0: rows = grad_out[b,ch,:].  MODE 1: rows = g1 = grad_ee[b,c+ch,:],
-// plus the central term sum_s (g0 - g1)[i,s] read in place.  MODE 2 (interpolation backward): the lists hold entries
-// e = 3 j + t of idx[b, 3 rowlen], the contribution of an entry is fmul(rows[ch][e / 3], wgt[b][e]).
-template <int CC, int MODE>
-__global__ void __launch_bounds__(1024, 1) pull_stream_kernel(const float* __restrict__ src, const int* __restrict__ offs,
-                                                          const int* __restrict__ pos, int c, int ntargets, int rowlen, int k,
-                                                          int chunks_per_cta, float* __restrict__ dst,
-                                                          const float* __restrict__ wgt) {
-    constexpr int NR = MODE == 1 ? 2 * CC : CC;    // rows staged per chunk (MODE 1: CC g0 rows, then CC g1 rows)
-    constexpr int ECACHE = PDGN_PULL_ECACHE;       // list entries cached in registers across the chunks
-    extern __shared__ __align__(128) float buf[];  // [2][NR*rowlen]
-    __shared__ uint64_t bars[2];
-    __shared__ int nlong, longlist[512];
-    const int bz = blockIdx.y, tid = threadIdx.x;
-    const int nchunks = (c + CC - 1) / CC;
-    const int chunk0 = blockIdx.x * chunks_per_cta;
-    const int nloc = min(nchunks, chunk0 + chunks_per_cta) - chunk0;
-    if (nloc <= 0) return;
-    const float* g0_b = src + (size_t)bz * 2 * c * rowlen;                                  // MODE 1 only
-    const float* rows_b = MODE != 1 ? src + (size_t)bz * c * rowlen : g0_b + (size_t)c * rowlen;
-    float* dst_b = dst + (size_t)bz * c * ntargets;
-    const int* ob = offs + (size_t)bz * (ntargets + 1);
-    const int* pb = pos + (size_t)bz * rowlen * (MODE == 2 ? 3 : 1);
-    const float* wb = MODE == 2 ? wgt + (size_t)bz * rowlen * 3 : nullptr;
-    // contribution of list entry e to channel ch of the staged chunk
-    auto contrib = [&](const float* rows, int ch, int e) {
-        return MODE == 2 ? __fmul_rn(rows[ch * rowlen + e / 3], __ldg(wb + e)) : rows[ch * rowlen + e];
-    };
-    auto issue = [&](int i) {
-        const int ch0 = (chunk0 + i) * CC;
-        const unsigned bytes = (unsigned)min(CC, c - ch0) * (unsigned)rowlen * 4u;
-        float* d = buf + (size_t)(i & 1) * NR * rowlen;
-        mbar_expect_tx(&bars[i & 1], MODE == 1 ? 2u * bytes : bytes);
-        if (MODE == 1) bulk_g2s(d, g0_b + (size_t)ch0 * rowlen, bytes, &bars[i & 1]);
-        bulk_g2s(d + (MODE == 1 ? CC * rowlen : 0), rows_b + (size_t)ch0 * rowlen, bytes, &bars[i & 1]);
-    };
-    if (tid == 0) {
-        mbar_init(&bars[0], 1);
-        mbar_init(&bars[1], 1);
-        mbar_fence_init();
-        nlong = 0;
-    }
-    __syncthreads();
-    if (tid == 0) {
-        issue(0);
-        if (nloc > 1) issue(1);
-    }
-    const int lane = tid & 31, warp = tid >> 5;
-    // the inverse-index list of a target is the same for every chunk: thread tid keeps (up to ECACHE entries of) the
-    // list of target tid in registers, so the per-chunk work is shared-memory gathers only
-    const bool single = ntargets <= 1024;
-    int ca = 0, clen = 0, ec[ECACHE];
-    float wc[MODE == 2 ? ECACHE : 1];
-    if (single && tid < ntargets) {
-        ca = ob[tid];
-        clen = ob[tid + 1] - ca;
-    }
-#pragma unroll
-    for (int u = 0; u < ECACHE; ++u) {
-        const int e = (single && u < clen && clen <= ECACHE) ? __ldg(pb + ca + u) : 0;
-        ec[u] = MODE == 2 ? e / 3 : e;
-        if (MODE == 2) wc[u] = __ldg(wb + e);
-    }
-
-    for (int i = 0; i < nloc; ++i) {
-        const int ch0 = (chunk0 + i) * CC;
-        const int cc = min(CC, c - ch0);
-        const float* stage = buf + (size_t)(i & 1) * NR * rowlen;
-        const float* rows = stage + (MODE == 1 ? CC * rowlen : 0);
-        mbar_wait(&bars[i & 1], (unsigned)((i >> 1) & 1));
-        for (int p = tid; p < ntargets; p += 1024) {
-            const int a = single ? ca : ob[p];
-            const int len = single ? clen : ob[p + 1] - a;
-            // the caller's buffer is ADDED into: read it now (coalesced), so the load latency hides under the list walk;
-            // every (channel, target) is written by exactly one thread => plain store, no atomics
-            float acc[CC], old[CC];
-#pragma unroll
-            for (int ch = 0; ch < CC; ++ch) old[ch] = ch < cc ? dst_b[(size_t)(ch0 + ch) * ntargets + p] : 0.f;
-#pragma unroll
-            for (int ch = 0; ch < CC; ++ch) {
-                acc[ch] = 0.f;
-                if (MODE == 1) {
-                    const float* r0 = stage + ch * rowlen + p * k;
-                    const float* r1 = rows + ch * rowlen + p * k;
-                    for (int s = 0; s < k; ++s) acc[ch] += r0[s] - r1[s];
-                }
-            }
-            if (single && len <= ECACHE) {
-#pragma unroll
-                for (int u = 0; u < ECACHE; ++u)
-                    if (u < len) {
-#pragma unroll
-                        for (int ch = 0; ch < CC; ++ch)
-                            acc[ch] += MODE == 2 ? __fmul_rn(rows[ch * rowlen + ec[u]], wc[u]) : rows[ch * rowlen + ec[u]];
-                    }
-            } else if (len > PULL_LONG) {
-                const int slot = atomicAdd(&nlong, 1);
-                if (slot < 512) longlist[slot] = p;  // the warp pass below adds the list sum after this thread's store
-                else pull_list<CC>(pb, a, a + len, acc, [&](int ch, int e) { return contrib(rows, ch, e); });
-            } else {
-                pull_list<CC>(pb, a, a + len, acc, [&](int ch, int e) { return contrib(rows, ch, e); });
-            }
-#pragma unroll
-            for (int ch = 0; ch < CC; ++ch)
-                if (ch < cc) dst_b[(size_t)(ch0 + ch) * ntargets + p] = old[ch] + acc[ch];
-        }
-        __syncthreads();
-        const int nl = min(nlong, 512);
-        for (int j = warp; j < nl; j += 32) {
-            const int p = longlist[j];
-            float acc[CC];
-#pragma unroll
-            for (int ch = 0; ch < CC; ++ch) acc[ch] = 0.f;
-            pull_list_warp<CC>(pb, ob[p], ob[p + 1], lane, acc, [&](int ch, int e) { return contrib(rows, ch, e); });
-            if (lane == 0) {
-#pragma unroll
-                for (int ch = 0; ch < CC; ++ch)
-                    if (ch < cc) dst_b[(size_t)(ch0 + ch) * ntargets + p] += acc[ch];
-            }
-        }
-        __syncthreads();  // buffer (i&1) and longlist are free again
-        if (tid == 0) {
-            nlong = 0;
-            if (i + 2 < nloc) {
-                fence_proxy_async();
-                issue(i + 2);
-            }
-        }
-        __syncthreads();
-    }
-}
-
-template <int MODE>
-static int launch_pull_stream(const float* src, const int* offs, const int* pos, int b, int c, int ntargets, int rowlen, int k,
-                              float* dst, cudaStream_t st, bool* launched, const float* wgt = nullptr) {
-    *launched = false;
-    const size_t row_bytes = (size_t)rowlen * 4;
-    if ((rowlen & 3) != 0 || (reinterpret_cast<uintptr_t>(src) & 15) != 0 || 2 * row_bytes > 200 * 1024) return PDGN_OK;
-    const size_t per_cc = (MODE == 1 ? 4 : 2) * row_bytes;  // double-buffered bytes per staged channel
-    if (per_cc > 200 * 1024) return PDGN_OK;
-    const int CCsel = (4 * per_cc <= 200 * 1024 && c >= 4) ? 4 : (2 * per_cc <= 200 * 1024 && c >= 2) ? 2 : 1;
-    const int nchunks = (c + CCsel - 1) / CCsel;
-    int sms = 148;
-    int cpc = (int)(((long long)nchunks * b + 2 * sms - 1) / (2 * sms));
-    if (cpc < 1) cpc = 1;
-    dim3 grid((nchunks + cpc - 1) / cpc, b);
-    const size_t smem = (size_t)CCsel * per_cc;
-#define PDGN_LAUNCH_PULL(CC_)                                                                                                   \
-    do {                                                                                                                        \
-        PDGN_CUDA(cudaFuncSetAttribute(pull_stream_kernel<CC_, MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
-        pull_stream_kernel<CC_, MODE><<<grid, 1024, smem, st>>>(src, offs, pos, c, ntargets, rowlen, k, cpc, dst, wgt);         \
-    } while (0)
-    if (CCsel == 4) PDGN_LAUNCH_PULL(4);
-    else if (CCsel == 2) PDGN_LAUNCH_PULL(2);
-    else PDGN_LAUNCH_PULL(1);
-#undef PDGN_LAUNCH_PULL
-    PDGN_CHECK_LAUNCH();
-    *launched = true;
-    return PDGN_OK;
 }
 
 // ---------------------------------------------------------------- interpolation forward
@@ -771,8 +605,8 @@ extern "C" int pdgn_group_bwd_ws(const float* grad_out, const int* idx, int b, i
     PDGN_VERIFY_IDX32(idx, (size_t)b * m * k, n, (cudaStream_t)stream);
     if (mk > 0x7fffffffLL || b > 65535) return PDGN_ERR_UNSUPPORTED;
     const size_t row_bytes = (size_t)mk * 4;
-    const size_t csr_smem = ((size_t)2 * n + 32) * sizeof(int);
-    if (!workspace || c < 4 || row_bytes > 200 * 1024 || csr_smem > 200 * 1024)
+    const size_t csr_smem = csr_smem_bytes(n);
+    if (!workspace || c < 4 || row_bytes > 200 * 1024 || !csr_ok(n, mk))
         return pdgn_group_bwd(grad_out, idx, b, c, n, m, k, grad_points, stream);
     if (workspace_bytes < pdgn_group_bwd_workspace(b, n, m, k) - 256 || (reinterpret_cast<uintptr_t>(workspace) & 3)) return PDGN_ERR_WORKSPACE;
     cudaStream_t st = (cudaStream_t)stream;
@@ -782,7 +616,7 @@ extern "C" int pdgn_group_bwd_ws(const float* grad_out, const int* idx, int b, i
     csr_build_kernel<int><<<b, CSR_T, csr_smem, st>>>(idx, n, (int)mk, offs, pos);
     PDGN_CHECK_LAUNCH();
     bool launched = false;
-    const int rc_stream = launch_pull_stream<0>(grad_out, offs, pos, b, c, n, (int)mk, 0, grad_points, st, &launched);
+    const int rc_stream = pull_stream_launch(0, grad_out, offs, pos, b, c, n, (int)mk, 0, grad_points, st, &launched, nullptr);
     if (rc_stream != PDGN_OK || launched) return rc_stream;
     int cc = 1;
     while (cc < 4 && (size_t)cc * 2 * row_bytes <= 100 * 1024) cc *= 2;
@@ -868,11 +702,11 @@ extern "C" int pdgn_interp_bwd_ws(const float* grad_out, const int* idx, const f
     PDGN_GATHER_ARGS_OK(grad_out && idx && weight && grad_points && m > 0);
     PDGN_VERIFY_IDX32(idx, (size_t)b * n * 3, m, (cudaStream_t)stream);
     if (b > 65535) return PDGN_ERR_UNSUPPORTED;
-    const size_t csr_smem = ((size_t)2 * m + 32) * sizeof(int);
+    const size_t csr_smem = csr_smem_bytes(m);
     int cc = PULL_CC;
     while (cc > 1 && ((size_t)cc * n + 3 * (size_t)n) * 4 > 96 * 1024) cc >>= 1;
     const size_t smem = ((size_t)cc * n + 3 * (size_t)n) * 4;
-    if (!workspace || c < 4 || smem > 200 * 1024 || csr_smem > 200 * 1024 || (long long)n * 3 > 0x7fffffffLL)
+    if (!workspace || c < 4 || smem > 200 * 1024 || !csr_ok(m, (long long)n * 3))
         return pdgn_interp_bwd(grad_out, idx, weight, b, c, n, m, grad_points, stream);
     if (workspace_bytes < pdgn_interp_bwd_workspace(b, n, m) - 256 || (reinterpret_cast<uintptr_t>(workspace) & 3)) return PDGN_ERR_WORKSPACE;
     cudaStream_t st = (cudaStream_t)stream;
@@ -883,7 +717,7 @@ extern "C" int pdgn_interp_bwd_ws(const float* grad_out, const int* idx, const f
     PDGN_CHECK_LAUNCH();
     {   // streaming form (TMA double-buffered rows, register-cached lists and weights): any shape it accepts
         bool launched = false;
-        const int rc = launch_pull_stream<2>(grad_out, offs, pos, b, c, m, n, 3, grad_points, st, &launched, weight);
+        const int rc = pull_stream_launch(2, grad_out, offs, pos, b, c, m, n, 3, grad_points, st, &launched, weight);
         if (rc != PDGN_OK) return rc;
         if (launched) return PDGN_OK;
     }
@@ -963,9 +797,9 @@ extern "C" int pdgn_edge_feat_bwd_ws(const float* grad_ee, const int64_t* idx, i
     PDGN_VERIFY_IDX64(idx, (size_t)b * n * k, n, (cudaStream_t)stream);
     if (b > 65535) return PDGN_ERR_UNSUPPORTED;
     const long long nk = (long long)n * k;
-    const size_t csr_smem = ((size_t)2 * n + 32) * sizeof(int);
+    const size_t csr_smem = csr_smem_bytes(n);
     const size_t row_bytes = (size_t)nk * 4;  // the g1 row of one channel
-    if (!workspace || row_bytes > 200 * 1024 || csr_smem > 200 * 1024 || nk > 0x7fffffffLL)
+    if (!workspace || row_bytes > 200 * 1024 || !csr_ok(n, nk))
         return pdgn_edge_feat_bwd(grad_ee, idx, b, c, n, k, grad_x, stream);
     if (workspace_bytes < pdgn_edge_feat_bwd_workspace(b, n, k) - 256 || (reinterpret_cast<uintptr_t>(workspace) & 3)) return PDGN_ERR_WORKSPACE;
     cudaStream_t st = (cudaStream_t)stream;
@@ -975,7 +809,7 @@ extern "C" int pdgn_edge_feat_bwd_ws(const float* grad_ee, const int64_t* idx, i
     csr_build_kernel<long long><<<b, CSR_T, csr_smem, st>>>(reinterpret_cast<const long long*>(idx), n, (int)nk, offs, pos);
     PDGN_CHECK_LAUNCH();
     bool launched = false;
-    const int rc_stream = launch_pull_stream<1>(grad_ee, offs, pos, b, c, n, (int)nk, k, grad_x, st, &launched);
+    const int rc_stream = pull_stream_launch(1, grad_ee, offs, pos, b, c, n, (int)nk, k, grad_x, st, &launched, nullptr);
     if (rc_stream != PDGN_OK || launched) return rc_stream;
     int cc = 1;
     while (cc < 4 && (size_t)cc * 2 * row_bytes <= 100 * 1024) cc *= 2;

@@ -960,3 +960,53 @@ print('dup ok')
         env = dict(os.environ, PDGN_B200_TUNE="1", PDGN_KNN_IMPL=impl)
         r = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, timeout=900, env=env)
         assert r.returncode == 0 and "dup ok" in r.stdout, impl + "\n" + r.stdout[-2000:] + r.stderr[-3000:]
+
+
+def _hub_idx(rng, b, n, count, hubs):
+    """Index tensor with a skewed in-degree distribution: a third of the entries point at a handful of hub targets (feature-
+    space kNN graphs look like this), a few targets are never referenced, the rest is uniform."""
+    idx = rng.integers(n // 8, n, (b, count)).astype(np.int32)          # targets below n/8 stay empty ...
+    hot = rng.random((b, count)) < 0.33
+    idx[hot] = rng.integers(0, hubs, int(hot.sum())).astype(np.int32)   # ... except the hubs
+    return idx
+
+
+@pytest.mark.parametrize("b,c,n,m,k", [(5, 64, 1024, 1024, 10), (9, 32, 128, 128, 10), (3, 20, 256, 300, 6), (4, 5, 2000, 1500, 4),
+                                       (7, 130, 512, 512, 10), (2, 12, 64, 700, 8), (40, 8, 96, 96, 10)])
+def test_streaming_pull_backward_hubs_groups_batches(dev, b, c, n, m, k):
+    """The streaming pull kernels behind grouping / edge-feature / interpolation backward (gather.cu: pull_stream_kernel +
+    csr_build_kernel): hub targets (lists far beyond the register cache, summed by whole warps), empty targets, channel groups
+    (n < 1024), more than 1024 targets, persistent CTAs crossing batch elements; close to the FP64-accumulated oracle and
+    bit-identical from run to run (the reference's atomicAdd is neither ordered nor reproducible)."""
+    from oracle import cpu as ocpu
+    from pdgn_b200 import ops
+    rng = np.random.default_rng(b * 131 + c)
+    idx = _hub_idx(rng, b, n, m * k, 5).reshape(b, m, k)
+    go = rng.standard_normal((b, c, m, k)).astype(np.float32)
+    g1 = ops.group_bwd(G(go, dev), G(idx, dev), n)
+    ref = ocpu.group_bwd(go, idx, n)
+    # tolerance: a few FP32 ulps of the sum of |contributions| of each target (2e-6 of it: stricter than 1e-5 relative wherever
+    # the terms do not cancel, and meaningful for the hubs whose hundreds of terms do)
+    assert np.all(np.abs(C(g1) - ref) <= 2e-6 * ocpu.group_bwd(np.abs(go), idx, n) + 1e-7)
+    assert torch.equal(g1, ops.group_bwd(G(go, dev), G(idx, dev), n))
+    # interpolation backward: n outputs interpolate m_t targets
+    m_t = n
+    idx3 = _hub_idx(rng, b, m_t, m * 3, 3).reshape(b, m, 3)
+    w = rng.uniform(0, 1, (b, m, 3)).astype(np.float32)
+    go3 = rng.standard_normal((b, c, m)).astype(np.float32)
+    g3 = ops.interp_bwd(G(go3, dev), G(idx3, dev), G(w, dev), m_t)
+    ref3 = ocpu.interp_bwd(go3, idx3, w, m_t)
+    assert np.all(np.abs(C(g3) - ref3) <= 2e-6 * ocpu.interp_bwd(np.abs(go3), idx3, w, m_t) + 1e-7)
+    assert torch.equal(g3, ops.interp_bwd(G(go3, dev), G(idx3, dev), G(w, dev), m_t))
+    # edge features backward (square graph: n points, k neighbours each), against torch autograd through the restated gather
+    from oracle import torch_ref as tref
+    idxe = _hub_idx(rng, b, n, n * k, 4).reshape(b, n, k).astype(np.int64)
+    gee = rng.standard_normal((b, 2 * c, n, k)).astype(np.float32)
+    ge = ops.edge_feat_bwd(G(gee, dev), torch.from_numpy(idxe).to(dev), c)
+    xr = torch.zeros((b, c, n), dtype=torch.float64, requires_grad=True)
+    (tref.edge_features_from_idx(xr, torch.from_numpy(idxe), k) * torch.from_numpy(gee).double()).sum().backward()
+    refe = xr.grad.numpy()
+    age = np.abs(gee)
+    scale = age[:, :c].sum(-1) + age[:, c:].sum(-1) + ocpu.group_bwd(np.ascontiguousarray(age[:, c:]), idxe.astype(np.int32), n)
+    assert np.all(np.abs(C(ge) - refe) <= 2e-6 * scale + 1e-7)
+    assert torch.equal(ge, ops.edge_feat_bwd(G(gee, dev), torch.from_numpy(idxe).to(dev), c))

@@ -14,3 +14,9 @@ for _ in range(2):
     ops.edge_feat_bwd(gee, idx.long(), c)
     ops.group_bwd(go, idx, n)
 torch.cuda.synchronize()
+w3 = torch.rand(b, 2 * n, 3, device=dev)
+idx3 = torch.from_numpy(rng.integers(0, n, (b, 2 * n, 3)).astype(np.int32)).to(dev)
+go3 = torch.randn(b, c, 2 * n, device=dev)
+for _ in range(2):
+    ops.interp_bwd(go3, idx3, w3, n)
+torch.cuda.synchronize()
