@@ -179,6 +179,14 @@ int pdgn_shape_loss_bwd(int b, int levels, const int *npts, int k, const float *
  * direct distances d2(i,j) = sum_c (x[c,i]-x[c,j])^2 accumulated as an fma chain over c (skip=1 reproduces
  * the reference's "drop rank 0").  dist2 f32 [b,n,k] may be NULL.  skip+k <= min(n, 64). */
 int pdgn_knn_feat(const float *x, int b, int c, int n, int k, int skip, int64_t *idx, float *dist2, void *stream);
+/* Workspace form of pdgn_knn_feat (same results): for 8 <= c <= 256 (c % 8 == 0), 128 <= n <= 4096 (n % 128 == 0), k + skip <= 20
+ * the pairwise work runs on the tensor cores (tcgen05 TF32 Gram tiles as a FILTER with rigorous margins) and only the ~13
+ * surviving candidates of a query are re-ranked with the exact FP32 chain; other shapes take pdgn_knn_feat's kernel.
+ * Replaces the same torch.bmm + torch.sort (models/PDGNet_v2.py:449-459, :492-502).  workspace: device memory of
+ * pdgn_knn_feat_workspace(b, c, n) bytes. */
+size_t pdgn_knn_feat_workspace(int b, int c, int n);
+int pdgn_knn_feat_ws(const float *x, int b, int c, int n, int k, int skip, int64_t *idx, float *dist2, void *workspace,
+                     size_t workspace_bytes, void *stream);
 
 /* Edge-feature gather: replaces the index_select loop + repeat + cat (PDGNet_v2.py:461-477, :505-525).
  * x [b,c,n], idx int64 [b,n,k] -> ee [b,2c,n,k] = cat(x_i broadcast over k, x_idx - x_i) on dim 1.

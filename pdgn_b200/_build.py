@@ -7,7 +7,7 @@ from concurrent.futures import ThreadPoolExecutor
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 SO = os.path.join(HERE, "libpdgn_b200.so")
-SOURCES = ["api.cu", "knn_xyz.cu", "knn_gram.cu", "gather.cu", "pull_stream.cu", "chamfer.cu", "cd_allpairs.cu", "knn_feat.cu", "emd.cu", "local_stats.cu", "local_pair.cu", "shape_loss.cu", "verify.cu"]
+SOURCES = ["api.cu", "knn_xyz.cu", "knn_gram.cu", "gather.cu", "pull_stream.cu", "chamfer.cu", "cd_allpairs.cu", "knn_feat.cu", "knn_feat_tc.cu", "emd.cu", "local_stats.cu", "local_pair.cu", "shape_loss.cu", "verify.cu"]
 NVCC_FLAGS = ["-O3", "-std=c++17", "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-Xcompiler", "-fPIC"]
 
 

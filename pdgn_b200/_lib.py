@@ -47,6 +47,8 @@ SIGNATURES = {
     "pdgn_shape_loss_fwd": (_I, [_P, _I, _I, _P, _I, _P, _P, _SZ, _P]),
     "pdgn_shape_loss_bwd": (_I, [_I, _I, _P, _I, _P, _P, _P, _SZ, _P]),
     "pdgn_knn_feat": (_I, [_P, _I, _I, _I, _I, _I, _P, _P, _P]),
+    "pdgn_knn_feat_workspace": (_SZ, [_I, _I, _I]),
+    "pdgn_knn_feat_ws": (_I, [_P, _I, _I, _I, _I, _I, _P, _P, _P, _SZ, _P]),
     "pdgn_edge_feat_fwd": (_I, [_P, _P, _I, _I, _I, _I, _P, _P]),
     "pdgn_edge_feat_bwd": (_I, [_P, _P, _I, _I, _I, _I, _P, _P]),
     "pdgn_edge_feat_bwd_workspace": (_SZ, [_I, _I, _I]),

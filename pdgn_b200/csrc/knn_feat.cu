@@ -19,8 +19,11 @@ constexpr int FT = 256;   // threads
 constexpr int FB = 64;    // block edge (queries per CTA, candidates per tile)
 constexpr int FCK = 32;   // channels staged per step
 
+// flags != nullptr: only the queries with flags[b*n + i] < 0 are computed and written (the tensor-core path's overflow list);
+// a CTA without one returns at once.
 __global__ void __launch_bounds__(FT) knn_feat_kernel(const float* __restrict__ x, int c, int n, int k, int skip,
-                                                     long long* __restrict__ idx, float* __restrict__ dist2) {
+                                                     long long* __restrict__ idx, float* __restrict__ dist2,
+                                                     const int* __restrict__ flags) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     float* xi = reinterpret_cast<float*>(smem_raw);  // [FCK][FB]
     float* xj = xi + FCK * FB;                       // [FCK][FB]
@@ -33,6 +36,11 @@ __global__ void __launch_bounds__(FT) knn_feat_kernel(const float* __restrict__ 
     const int i0 = blockIdx.x * FB;
     const int ty = t >> 4, tx = t & 15;
     const float* xb = x + (size_t)bz * c * n;
+    bool mine = true;
+    if (flags) {
+        mine = t < FB && i0 + t < n && flags[(size_t)bz * n + i0 + t] < 0;
+        if (!__syncthreads_or(mine ? 1 : 0)) return;
+    }
 
     if (t < FB)
         for (int e = 0; e < kk; ++e) {
@@ -88,7 +96,7 @@ __global__ void __launch_bounds__(FT) knn_feat_kernel(const float* __restrict__ 
             }
         }
     }
-    if (t < FB && i0 + t < n) {
+    if (t < FB && i0 + t < n && mine) {
         const size_t o = ((size_t)bz * n + i0 + t) * k;
         for (int e = 0; e < k; ++e) {
             idx[o + e] = li[(skip + e) * FB + t];
@@ -110,7 +118,40 @@ extern "C" int pdgn_knn_feat(const float* x, int b, int c, int n, int k, int ski
     const size_t smem = (size_t)(2 * FCK * FB + FB * (FB + 1)) * 4 + (size_t)(k + skip) * FB * 8;
     PDGN_CUDA(cudaFuncSetAttribute(knn_feat_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     dim3 grid((n + FB - 1) / FB, b);
-    knn_feat_kernel<<<grid, FT, smem, (cudaStream_t)stream>>>(x, c, n, k, skip, reinterpret_cast<long long*>(idx), dist2);
+    knn_feat_kernel<<<grid, FT, smem, (cudaStream_t)stream>>>(x, c, n, k, skip, reinterpret_cast<long long*>(idx), dist2, nullptr);
+    PDGN_CHECK_LAUNCH();
+    return PDGN_OK;
+}
+
+namespace pdgn {
+bool knn_feat_tc_eligible(int c, int n, int k, int skip);
+size_t knn_feat_tc_workspace(int b, int c, int n);
+int knn_feat_tc_launch(const float* x, int b, int c, int n, int k, int skip, long long* idx, float* dist2, void* ws, const int** flags,
+                       cudaStream_t st);
+}  // namespace pdgn
+
+// Workspace form: the tensor-core filter + exact re-rank of knn_feat_tc.cu for the shapes it takes (8 <= c <= 256, c % 8 == 0,
+// 128 <= n <= 4096, n % 128 == 0, k + skip <= 20), the kernel above otherwise.  Same results either way.
+extern "C" size_t pdgn_knn_feat_workspace(int b, int c, int n) {
+    if (b < 0 || c < 1 || n < 0) return 0;
+    return knn_feat_tc_workspace(b, c, n);
+}
+
+extern "C" int pdgn_knn_feat_ws(const float* x, int b, int c, int n, int k, int skip, int64_t* idx, float* dist2, void* workspace,
+                                size_t workspace_bytes, void* stream) {
+    PDGN_RANGE("pdgn_knn_feat_ws");
+    if (!x || !idx || b < 0 || c < 1 || n < 0 || k < 1 || skip < 0) return PDGN_ERR_BAD_ARG;
+    static const char* impl = tune_env("PDGN_KNN_FEAT_IMPL");      // "simt": always the FP32 SIMT kernel (A/B runs)
+    if (!workspace || !knn_feat_tc_eligible(c, n, k, skip) || b > 65535 || b == 0 || (impl && impl[0] == 's'))
+        return pdgn_knn_feat(x, b, c, n, k, skip, idx, dist2, stream);
+    if (workspace_bytes < knn_feat_tc_workspace(b, c, n) - 256) return PDGN_ERR_WORKSPACE;
+    const int* flags = nullptr;
+    const int rc = knn_feat_tc_launch(x, b, c, n, k, skip, reinterpret_cast<long long*>(idx), dist2, workspace, &flags, (cudaStream_t)stream);
+    if (rc != PDGN_OK) return rc;
+    const size_t smem = (size_t)(2 * FCK * FB + FB * (FB + 1)) * 4 + (size_t)(k + skip) * FB * 8;
+    PDGN_CUDA(cudaFuncSetAttribute(knn_feat_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    dim3 grid((n + FB - 1) / FB, b);
+    knn_feat_kernel<<<grid, FT, smem, (cudaStream_t)stream>>>(x, c, n, k, skip, reinterpret_cast<long long*>(idx), dist2, flags);
     PDGN_CHECK_LAUNCH();
     return PDGN_OK;
 }

@@ -21,6 +21,7 @@
 //            the warp through the 64-bit network instead.  Survivor overflow (duplicates, clusters, fewer than k finite
 //            candidates) goes to a warp-cooperative exact selection, so the result never depends on the heuristics.
 #include "common.cuh"
+#include "selnet.cuh"
 
 namespace pdgn {
 
@@ -39,9 +40,6 @@ constexpr int KQ_KMAX = 20;
 static_assert(KQ_BLK >= 64 * 32 * 4, "sub-minimum words must fit the block");
 
 __device__ __forceinline__ int kq_pad(int pos) { return pos + ((pos >> 5) << 2); }
-__device__ __forceinline__ unsigned kq_min2(unsigned a, unsigned b) { unsigned r; asm("min.u16x2 %0, %1, %2;" : "=r"(r) : "r"(a), "r"(b)); return r; }
-__device__ __forceinline__ unsigned kq_max2(unsigned a, unsigned b) { unsigned r; asm("max.u16x2 %0, %1, %2;" : "=r"(r) : "r"(a), "r"(b)); return r; }
-
 // Error margin of the pass-1 value h = fl(g + |q|^2), g = fl(|p|^2 - 2 q.p) (3 FFMA on a 3-rounding |p|^2), against the
 // reference's computed d_ref.  With u = 2^-24: |g - (|p|^2 - 2 q.p)| <= 3u|p|^2 + 3u(|p|^2 + 2|q||p|), |fl(|q|^2) - |q|^2| <= 3u|q|^2,
 // the final add contributes u(|p|+|q|)^2, and |d_ref - |q-p|^2| <= 5.1u|q-p|^2: in total < 15.1u(|p|+|q|)^2.
@@ -49,34 +47,6 @@ __device__ __forceinline__ unsigned kq_max2(unsigned a, unsigned b) { unsigned r
 __device__ __forceinline__ float kq_margin(float pmax2, float qq) {
     const float s = __fadd_ru(__fsqrt_ru(pmax2), __fsqrt_ru(qq));
     return __fmul_ru(1.2e-6f, __fmul_ru(s, s));
-}
-
-// ascending bitonic sort of N registers with the given compare-exchange
-template <int N, typename CE>
-__device__ __forceinline__ void kq_bitonic_sort(CE ce) {
-#pragma unroll
-    for (int size = 2; size <= N; size <<= 1) {
-#pragma unroll
-        for (int stride = size >> 1; stride > 0; stride >>= 1) {
-#pragma unroll
-            for (int i = 0; i < N; ++i) {
-                const int p = i ^ stride;
-                if (p > i) ce(i, p, (i & size) == 0 || size == N);
-            }
-        }
-    }
-}
-// ascending bitonic MERGE of a bitonic sequence of N registers
-template <int N, typename CE>
-__device__ __forceinline__ void kq_bitonic_merge(CE ce) {
-#pragma unroll
-    for (int stride = N >> 1; stride > 0; stride >>= 1) {
-#pragma unroll
-        for (int i = 0; i < N; ++i) {
-            const int p = i ^ stride;
-            if (p > i) ce(i, p, true);
-        }
-    }
 }
 
 // k-th smallest (k <= 32) of the 64 group minima of one query.  words[e] (e < 64, stride 32 words) = (sub e) | (sub e+64) << 16.

@@ -203,9 +203,12 @@ def knn_feat(x, k, skip=1, return_dist=False):
     b, c, n = x.shape
     idx = torch.empty((b, n, k), dtype=torch.int64, device=x.device)
     dist2 = torch.empty((b, n, k), dtype=torch.float32, device=x.device) if return_dist else None
+    L = lib()
+    ws_bytes = L.pdgn_knn_feat_workspace(b, c, n)
+    ws = torch.empty((ws_bytes,), dtype=torch.uint8, device=x.device)
     with torch.cuda.device(x.device):
-        check(lib().pdgn_knn_feat(x.data_ptr(), b, c, n, int(k), int(skip), idx.data_ptr(),
-                                  dist2.data_ptr() if return_dist else None, _stream(x)), "pdgn_knn_feat")
+        check(L.pdgn_knn_feat_ws(x.data_ptr(), b, c, n, int(k), int(skip), idx.data_ptr(),
+                                 dist2.data_ptr() if return_dist else None, ws.data_ptr(), ws_bytes, _stream(x)), "pdgn_knn_feat_ws")
     return (idx, dist2) if return_dist else idx
 
 
