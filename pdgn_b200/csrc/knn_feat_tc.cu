@@ -31,8 +31,9 @@
 namespace pdgn {
 
 constexpr int TF_M = 128;    // queries per CTA = TMEM lanes
-constexpr int TF_N = 128;    // candidates per accumulator tile = TMEM columns = subgroups
+constexpr int TF_SG = 128;   // strided subgroups of the bound (candidate j -> subgroup j % 128); accumulator tiles are 128 or 256 wide
 constexpr int TF_KB = 32;    // channels per staged K-block (4 MMAs of K = 8)
+constexpr int TF_NST = 4;    // B ring stages (3 when the norms of a large cloud need the room)
 constexpr int TF_CAP = 32;   // list entries per query
 constexpr int TF_KMAX = 20;  // k + skip the bound network is tuned for (expected list: -ln(1 - k'/64) * 64 + margin)
 
@@ -61,7 +62,11 @@ __global__ void __launch_bounds__(256) kf_prep_kernel(const float* __restrict__ 
     __shared__ float part[8][32];
     const int bz = blockIdx.y, n0 = blockIdx.x * 32, tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
     const float* xb = x + (size_t)bz * c * n;
-    float* xcb = xc + (size_t)bz * n * c;   // centred rows, [n][c] like xT
+    // centred rows, PRE-TILED in the tensor core's operand order: one 16 KB block per (128 points, 32 channels), laid out
+    // [8-point group 16][4-channel chunk 8][point 8][4 floats] = the canonical K-major, no-swizzle UMMA core-matrix order, so
+    // a whole operand stage is ONE contiguous bulk copy.  Channels are padded with zeros to a multiple of 32.
+    const int nkb = (c + 31) >> 5;
+    float* xcb = xc + (size_t)bz * n * nkb * 32;
     float* xtb = xT + (size_t)bz * n * c;
     const float* mb = mean + (size_t)bz * c;
     float acc = 0.f;
@@ -78,9 +83,10 @@ __global__ void __launch_bounds__(256) kf_prep_kernel(const float* __restrict__ 
         }
         __syncthreads();
         for (int r = ty; r < 32; r += 8)
-            if (n0 + r < n && c0 + tx < c) {
-                xtb[(size_t)(n0 + r) * c + c0 + tx] = tile[tx][r];
-                xcb[(size_t)(n0 + r) * c + c0 + tx] = tilec[tx][r];
+            if (n0 + r < n) {
+                if (c0 + tx < c) xtb[(size_t)(n0 + r) * c + c0 + tx] = tile[tx][r];
+                const int pnt = n0 + r;
+                xcb[((size_t)(pnt >> 7) * nkb + (c0 >> 5)) * 4096 + ((pnt & 127) >> 3) * 256 + (tx >> 2) * 32 + (pnt & 7) * 4 + (tx & 3)] = tilec[tx][r];
             }
         __syncthreads();
     }
@@ -102,8 +108,8 @@ __device__ __forceinline__ uint64_t kf_desc(uint32_t saddr, uint32_t lbo_bytes, 
     // make up K = 8, SBO = bytes between 8-point groups.  Offsets in 16-byte units, descriptor version 1 (sm_100).
     return (uint64_t)((saddr & 0x3ffffu) >> 4) | ((uint64_t)(lbo_bytes >> 4) << 16) | ((uint64_t)(sbo_bytes >> 4) << 32) | (1ull << 46);
 }
-// instruction descriptor: D = F32, A = B = TF32, both K-major, N = 128, M = 128
-constexpr uint32_t KF_IDESC = (1u << 4) | (2u << 7) | (2u << 10) | ((TF_N >> 3) << 17) | ((TF_M >> 4) << 24);
+// instruction descriptor: D = F32, A = B = TF32, both K-major, N = tn, M = 128
+constexpr uint32_t kf_idesc(int tn) { return (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(tn >> 3) << 17) | ((uint32_t)(TF_M >> 4) << 24); }
 
 __device__ __forceinline__ void kf_mma(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t accumulate, uint32_t idesc) {
     asm volatile(
@@ -133,11 +139,6 @@ __device__ __forceinline__ void kf_tmem_ld32(uint32_t taddr, float (&v)[32]) {
 #pragma unroll
     for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(r[i]);
 }
-__device__ __forceinline__ void kf_cp16(uint32_t dst_s, const void* src) {
-    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst_s), "l"(src) : "memory");
-}
-__device__ __forceinline__ void kf_cp_wait_all() { asm volatile("cp.async.wait_all;" ::: "memory"); }
-
 // Bounds of one query.  ni = |xi|^2 and mx = max_j |xj|^2 of the centred, tf32-rounded rows; a16 = bf16 bits (rounded down) of
 // the k'-th smallest group minimum of h = ni + nj - 2 G.  With x~ the rounded rows and x^ = x - mean: |x~ - x^| <= 2^-11 |x^|
 // per component, so | |x~i - x~j| - |xi - xj| | <= eps = 2^-11 (|x^i| + |x^j|) <= 1.01 * 2^-11 (sqrt(ni) + sqrt(mx)), and the
@@ -160,44 +161,44 @@ __device__ __forceinline__ float kf_flag_threshold(unsigned a16, float ni, float
 
 // ---------------------------------------------------------------- filter
 // grid (n / 128, B), 128 threads.  Dynamic shared memory: A [c/8][32][128 B] | B stage 0, 1 [32][4][128 B] | norms [n] | lists.
+template <int TN>
 __global__ void __launch_bounds__(TF_M, 1) knn_feat_tc_kernel(const float* __restrict__ xc, const float* __restrict__ nrm,
                                                             const unsigned* __restrict__ maxn, int c, int n, int kk,
-                                                            int* __restrict__ cand, int* __restrict__ cnt, float* __restrict__ dbg, uint32_t idesc) {
+                                                            int* __restrict__ cand, int* __restrict__ cnt, int nst, float* __restrict__ dbg, uint32_t idesc) {
     extern __shared__ __align__(128) unsigned char kf_smem[];
-    __shared__ uint64_t bars[2];
+    __shared__ uint64_t bars[TF_NST], fullb[TF_NST], abar, tileb;   // bars: stage consumed by the tensor core; fullb: stage filled
     __shared__ uint32_t tmem_slot;
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const int bz = blockIdx.y, m0 = blockIdx.x * TF_M;
-    const int chunks = c >> 2;                                       // 16-byte channel chunks of a point
-    const uint32_t a_bytes = (uint32_t)TF_M * (uint32_t)c * 4u;
-    const uint32_t sbo_a = (uint32_t)chunks * 128u;                  // bytes between the 8-point groups of A
-    unsigned char* a_sm = kf_smem;
-    unsigned char* b_sm = a_sm + a_bytes;                            // 2 stages of 16 KB
-    float* nrm_s = reinterpret_cast<float*>(b_sm + 2 * 16384);       // [n]
+    const int nkb = (c + TF_KB - 1) / TF_KB;                          // K-blocks (channels zero-padded to a multiple of 32)
+    unsigned char* a_sm = kf_smem;                                   // nkb blocks of 16 KB: the CTA's 128 queries, all channels
+    constexpr int NB = TN / 128;                                     // 16 KB blocks (128 candidates x 32 channels) per stage
+    constexpr uint32_t SB = NB * 16384u;                             // bytes per ring stage
+    unsigned char* b_sm = a_sm + (size_t)nkb * 16384;                // nst ring stages
+    float* nrm_s = reinterpret_cast<float*>(b_sm + (size_t)nst * SB);   // [n]
     int* lst = reinterpret_cast<int*>(nrm_s + n);                    // [TF_CAP][128]
-    const float* xcb = xc + (size_t)bz * n * c;                      // centred, tf32-rounded rows [n][c]
+    const float* xcb = xc + (size_t)bz * n * nkb * 32;               // this batch element's pre-tiled blocks (kf_prep_kernel)
 
     if (tid == 0) {
-        mbar_init(&bars[0], 1);
-        mbar_init(&bars[1], 1);
-        mbar_fence_init();
+        for (int i = 0; i < nst; ++i) {
+            mbar_init(&bars[i], 1);
+            mbar_init(&fullb[i], 1);
+        }
+        mbar_init(&abar, 1);
+        mbar_init(&tileb, 1);        // one phase per accumulator tile: the threads that only meet the tensor core at a tile's end
+        mbar_fence_init();           // must not wait on a ring stage's barrier (two uses per tile would alias its phase parity)
     }
     if (warp == 0) {
-        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&tmem_slot)), "r"(128u) : "memory");
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&tmem_slot)), "r"((uint32_t)TN) : "memory");
         asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
     }
-    // A: every (point, 4 channels) piece of 16 bytes.  Piece p: r8 = p % 8, chunk = (p / 8) % chunks, 8-point group = rest --
-    // eight consecutive lanes fill one 128-byte core matrix (conflict-free) and a warp reads 8 points x 64 bytes of global memory.
-    {
-        const uint32_t a_s = smem_u32(a_sm);
-        for (int p = tid; p < TF_M * chunks; p += TF_M) {
-            const int r8 = p & 7, q = (p >> 3) % chunks, rg = (p >> 3) / chunks;
-            kf_cp16(a_s + (uint32_t)rg * sbo_a + (uint32_t)q * 128u + (uint32_t)r8 * 16u, xcb + (size_t)(m0 + rg * 8 + r8) * c + q * 4);
-        }
+    __syncthreads();
+    if (tid == 0) {                                                  // A: the query tile's blocks, one bulk copy each
+        mbar_expect_tx(&abar, (unsigned)nkb * 16384u);
+        for (int kb = 0; kb < nkb; ++kb)
+            bulk_g2s(a_sm + (size_t)kb * 16384, xcb + ((size_t)blockIdx.x * nkb + kb) * 4096, 16384u, &abar);
     }
     for (int j = tid; j < n; j += TF_M) nrm_s[j] = nrm[(size_t)bz * n + j];
-    kf_cp_wait_all();
-    fence_proxy_async();
     kf_fence_before();
     __syncthreads();
     kf_fence_after();
@@ -206,50 +207,81 @@ __global__ void __launch_bounds__(TF_M, 1) knn_feat_tc_kernel(const float* __res
 
     const float ni = nrm_s[m0 + tid];
     const float mx = __uint_as_float(maxn[bz]);
-    const int ntile = n / TF_N, nkb = (c + TF_KB - 1) / TF_KB;
-    float mn[TF_N];
+    const int ntile = n / TN;
+    float mn[TF_SG];
 #pragma unroll
-    for (int i = 0; i < TF_N; ++i) mn[i] = kInf;
+    for (int i = 0; i < TF_SG; ++i) mn[i] = kInf;
     float fv = 0.f;
     int nl = 0;
     bool over = false;
-    int it = 0;                                                      // staged K-blocks so far (ring position + phases)
-
+    // K-blocks of B, flattened over (pass, tile, K-block): iteration t uses ring stage t % nst.  Thread 0 is the producer AND
+    // the MMA issuer: one 16 KB bulk copy (TMA engine, completes on the stage's "full" mbarrier) per K-block, nst - 1 blocks ahead
+    // of the tensor core; four tcgen05.mma (K = 8 each) per block; tcgen05.commit releases the stage.  The other threads only
+    // meet the tensor core at the end of a tile.  (First version: 16-byte cp.async pieces from a row-major copy by all threads
+    // -- 1.1 us per K-block in the copy path alone, 2.6x slower overall.)
+    const int T = 2 * ntile * nkb;
+    int p_kb = 0, p_nt = 0, p_buf = 0, p_round = 0, p_left = T;     // producer cursor (thread 0)
+    auto issue_next = [&]() {
+        mbar_expect_tx(&fullb[p_buf], SB);
+#pragma unroll
+        for (int h = 0; h < NB; ++h)       // consecutive 128-candidate blocks are consecutive 8-point groups of one operand
+            bulk_g2s(b_sm + (size_t)p_buf * SB + (size_t)h * 16384, xcb + ((size_t)(p_nt * NB + h) * nkb + p_kb) * 4096, 16384u, &fullb[p_buf]);
+        if (++p_kb == nkb) {
+            p_kb = 0;
+            if (++p_nt == ntile) p_nt = 0;
+        }
+        if (++p_buf == nst) {
+            p_buf = 0;
+            ++p_round;
+        }
+        --p_left;
+    };
+    if (tid == 0) {
+        for (int t = 0; t < nst - 1; ++t)                            // all but one stage
+            if (p_left > 0) issue_next();
+        mbar_wait(&abar, 0u);
+    }
+    int buf = 0, round = 0;                                          // consumer: ring stage and how often it has been used
+    int tile_phase = 0;
+    const uint32_t a_s0 = smem_u32(a_sm), b_s0 = smem_u32(b_sm);
     for (int pass = 0; pass < 2; ++pass) {
         for (int nt = 0; nt < ntile; ++nt) {
-            for (int kb = 0; kb < nkb; ++kb, ++it) {
-                const int buf = it & 1;
-                if (it >= 2) mbar_wait(&bars[buf], (unsigned)(((it >> 1) - 1) & 1));   // the MMAs that read this stage are done
-                const int qs = min(8, chunks - kb * 8);             // 16-byte chunks of this K-block (even: c % 8 == 0)
-                const uint32_t b_s = smem_u32(b_sm + buf * 16384);
-                for (int p = tid; p < TF_N * qs; p += TF_M) {
-                    const int r8 = p & 7, q = (p >> 3) % qs, rg = (p >> 3) / qs;
-                    kf_cp16(b_s + (uint32_t)rg * 1024u + (uint32_t)q * 128u + (uint32_t)r8 * 16u,
-                            xcb + (size_t)(nt * TF_N + rg * 8 + r8) * c + kb * TF_KB + q * 4);
-                }
-                kf_cp_wait_all();
-                fence_proxy_async();
-                __syncthreads();
+            for (int kb = 0; kb < nkb; ++kb) {
                 if (tid == 0) {
+                    const uint32_t b_s = b_s0 + (uint32_t)buf * SB, a_s = a_s0 + (uint32_t)kb * 16384u;
+                    mbar_wait(&fullb[buf], (unsigned)(round & 1));   // the block has landed (async proxy: no proxy fence needed)
                     kf_fence_after();
-                    for (int kc = 0; kc < (qs >> 1); ++kc)
-                        kf_mma(tmem, kf_desc(smem_u32(a_sm) + (uint32_t)(kb * 8 + 2 * kc) * 128u, 128u, sbo_a),
-                               kf_desc(b_s + (uint32_t)(2 * kc) * 128u, 128u, 1024u), (kb | kc) ? 1u : 0u, idesc);
+#pragma unroll
+                    for (int kc = 0; kc < 4; ++kc)
+                        if (!(idesc & 1u))                           // idesc bit 0 (sparse id, unused): ablation without MMAs
+                            kf_mma(tmem, kf_desc(a_s + (uint32_t)kc * 256u, 128u, 1024u), kf_desc(b_s + (uint32_t)kc * 256u, 128u, 1024u),
+                                   (kb | kc) ? 1u : 0u, idesc);
                     kf_commit(&bars[buf]);
+                    if (kb == nkb - 1) kf_commit(&tileb);            // the tile's last commit covers every MMA issued before it
+                    // refill the stage the PREVIOUS iteration used, once its MMAs are done: this iteration's MMAs are already
+                    // queued behind them, so the tensor core does not idle while the issuer waits here
+                    if (p_left > 0) {
+                        if (p_round > 0) mbar_wait(&bars[p_buf], (unsigned)((p_round - 1) & 1));
+                        issue_next();
+                    }
+                }
+                if (++buf == nst) {
+                    buf = 0;
+                    ++round;
                 }
             }
-            // the tile's last commit covers every MMA issued before it
-            mbar_wait(&bars[(it - 1) & 1], (unsigned)(((it - 1) >> 1) & 1));
+            mbar_wait(&tileb, (unsigned)(tile_phase & 1));
+            ++tile_phase;
             kf_fence_after();
 #pragma unroll
-            for (int ch = 0; ch < TF_N / 32; ++ch) {
+            for (int ch = 0; ch < TN / 32; ++ch) {
                 float g[32];
                 kf_tmem_ld32(trow + (uint32_t)(ch * 32), g);
                 if (dbg && pass == 0 && nt == 0 && blockIdx.x == 0 && blockIdx.y == 0) {
 #pragma unroll
-                    for (int u = 0; u < 32; ++u) dbg[tid * TF_N + ch * 32 + u] = g[u] + 1000.f;
+                    for (int u = 0; u < 32; ++u) dbg[tid * TN + ch * 32 + u] = g[u] + 1000.f;
                 }
-                const float4* nj4 = reinterpret_cast<const float4*>(nrm_s + nt * TF_N + ch * 32);
+                const float4* nj4 = reinterpret_cast<const float4*>(nrm_s + nt * TN + ch * 32);
 #pragma unroll
                 for (int q = 0; q < 8; ++q) {
                     const float4 nj = nj4[q];
@@ -258,9 +290,9 @@ __global__ void __launch_bounds__(TF_M, 1) knn_feat_tc_kernel(const float* __res
                     for (int u = 0; u < 4; ++u) {
                         const float t = __fmaf_rn(-2.f, g[4 * q + u], njv[u]);
                         if (pass == 0) {
-                            mn[ch * 32 + 4 * q + u] = fminf(mn[ch * 32 + 4 * q + u], t);   // NaN never wins
+                            mn[(ch & 3) * 32 + 4 * q + u] = fminf(mn[(ch & 3) * 32 + 4 * q + u], t);   // NaN never wins
                         } else if (__fadd_rn(t, ni) <= fv) {
-                            if (nl < TF_CAP) lst[nl * TF_M + tid] = nt * TF_N + ch * 32 + 4 * q + u;
+                            if (nl < TF_CAP) lst[nl * TF_M + tid] = nt * TN + ch * 32 + 4 * q + u;
                             else over = true;
                             nl += nl < TF_CAP ? 1 : 0;
                         }
@@ -301,7 +333,7 @@ __global__ void __launch_bounds__(TF_M, 1) knn_feat_tc_kernel(const float* __res
     }
     kf_fence_before();
     __syncthreads();
-    if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"(128u) : "memory");
+    if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"((uint32_t)TN) : "memory");
 }
 
 // ---------------------------------------------------------------- exact re-rank: warp = query, lane = candidate
@@ -317,7 +349,31 @@ __global__ void __launch_bounds__(256) knn_feat_rerank_kernel(const float* __res
     const float* xi = xT + (size_t)q * c;
     const float* xj = xT + ((size_t)bz * n + max(j, 0)) * c;
     float acc = 0.f;
-    if ((c & 3) == 0) {
+    if (j < 0) {
+        // idle lane: no loads (the re-rank is bound by the L2 -> SM traffic of the candidate rows)
+    } else if ((c & 15) == 0) {
+        // 64 bytes of each row per step: four independent 16-byte loads in flight per lane (the kernel is bound by the L2 -> SM
+        // traffic of the candidate rows, ~14 KB per query); the chain itself stays strictly sequential in c
+        for (int ch = 0; ch < c; ch += 16) {
+            float4 a[4], b[4];
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+                a[u] = __ldg(reinterpret_cast<const float4*>(xi + ch) + u);
+                b[u] = __ldg(reinterpret_cast<const float4*>(xj + ch) + u);
+            }
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+                float d = __fsub_rn(a[u].x, b[u].x);
+                acc = __fmaf_rn(d, d, acc);
+                d = __fsub_rn(a[u].y, b[u].y);
+                acc = __fmaf_rn(d, d, acc);
+                d = __fsub_rn(a[u].z, b[u].z);
+                acc = __fmaf_rn(d, d, acc);
+                d = __fsub_rn(a[u].w, b[u].w);
+                acc = __fmaf_rn(d, d, acc);
+            }
+        }
+    } else if ((c & 3) == 0) {
         for (int ch = 0; ch < c; ch += 4) {
             const float4 a = __ldg(reinterpret_cast<const float4*>(xi + ch)), b = __ldg(reinterpret_cast<const float4*>(xj + ch));
             float d = __fsub_rn(a.x, b.x);
@@ -353,7 +409,8 @@ bool knn_feat_tc_eligible(int c, int n, int k, int skip) {
 }
 size_t knn_feat_tc_workspace(int b, int c, int n) {
     const size_t bc = (size_t)b * c, bn = (size_t)b * n;
-    return kf_align(bc * 4) + 2 * kf_align(bc * n * 4) + kf_align(bn * 4) + kf_align((size_t)b * 4) + kf_align(bn * TF_CAP * 4) + kf_align(bn * 4) + 256;
+    const size_t cp = (size_t)((c + 31) / 32) * 32;                 // channels padded to whole K-blocks in the tiled copy
+    return kf_align(bc * 4) + kf_align((size_t)b * cp * n * 4) + kf_align(bc * n * 4) + kf_align(bn * 4) + kf_align((size_t)b * 4) + kf_align(bn * TF_CAP * 4) + kf_align(bn * 4) + 256;
 }
 
 // Runs prep + filter + re-rank; *flags receives the per-query count array (negative = recompute with the exact kernel).
@@ -364,7 +421,7 @@ int knn_feat_tc_launch(const float* x, int b, int c, int n, int k, int skip, lon
     float* mean = reinterpret_cast<float*>(p);
     p += kf_align(bc * 4);
     float* xc = reinterpret_cast<float*>(p);
-    p += kf_align(bc * n * 4);
+    p += kf_align((size_t)b * ((c + 31) / 32) * 32 * n * 4);
     float* xT = reinterpret_cast<float*>(p);
     p += kf_align(bc * n * 4);
     float* nrm = reinterpret_cast<float*>(p);
@@ -379,11 +436,26 @@ int knn_feat_tc_launch(const float* x, int b, int c, int n, int k, int skip, lon
     PDGN_CHECK_LAUNCH();
     kf_prep_kernel<<<dim3((n + 31) / 32, b), 256, 0, st>>>(x, mean, c, n, xc, xT, nrm, maxn);
     PDGN_CHECK_LAUNCH();
-    const size_t smem = (size_t)TF_M * c * 4 + 2 * 16384 + (size_t)n * 4 + (size_t)TF_CAP * TF_M * 4;
-    PDGN_CUDA(cudaFuncSetAttribute(knn_feat_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    knn_feat_tc_kernel<<<dim3(n / TF_M, b), TF_M, smem, st>>>(xc, nrm, maxn, c, n, k + skip, cand, cnt,
-                                                                  tune_env("PDGN_KNN_FEAT_DBG") ? reinterpret_cast<float*>(cand) : nullptr,
-                                                                  tune_env("PDGN_KNN_FEAT_IDESC") ? (uint32_t)strtoul(tune_env("PDGN_KNN_FEAT_IDESC"), nullptr, 16) : KF_IDESC);
+    // accumulator tiles of 256 candidates when the cloud allows (half the tcgen05.mma count: the K = 8 instructions are issue /
+    // operand-fetch bound, ~0.26 us each at N = 128), ring as deep as shared memory allows (>= 2 stages)
+    const int tn = (n % 256 == 0 && n >= 1024) ? 256 : 128;   // small clouds: more, smaller tiles keep the ring deep
+    static const char* tn_env = tune_env("PDGN_KNN_FEAT_TN");
+    const int tnsel = (tn_env && atoi(tn_env) == 128) ? 128 : tn;
+    const size_t fixed = (size_t)((c + 31) / 32) * 16384 + (size_t)n * 4 + (size_t)TF_CAP * TF_M * 4, sb = (size_t)(tnsel / 128) * 16384;
+    int nst = (int)((216 * 1024 - fixed) / sb);
+    if (nst > TF_NST) nst = TF_NST;
+    if (nst < 2) return PDGN_ERR_UNSUPPORTED;
+    const size_t smem = fixed + (size_t)nst * sb;
+    float* dbg = tune_env("PDGN_KNN_FEAT_DBG") ? reinterpret_cast<float*>(cand) : nullptr;
+    uint32_t idesc = kf_idesc(tnsel);
+    if (tune_env("PDGN_KNN_FEAT_NOMMA")) idesc |= 1u;
+    if (tnsel == 256) {
+        PDGN_CUDA(cudaFuncSetAttribute(knn_feat_tc_kernel<256>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        knn_feat_tc_kernel<256><<<dim3(n / TF_M, b), TF_M, smem, st>>>(xc, nrm, maxn, c, n, k + skip, cand, cnt, nst, dbg, idesc);
+    } else {
+        PDGN_CUDA(cudaFuncSetAttribute(knn_feat_tc_kernel<128>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        knn_feat_tc_kernel<128><<<dim3(n / TF_M, b), TF_M, smem, st>>>(xc, nrm, maxn, c, n, k + skip, cand, cnt, nst, dbg, idesc);
+    }
     PDGN_CHECK_LAUNCH();
     knn_feat_rerank_kernel<<<(unsigned)((bn + 7) / 8), 256, 0, st>>>(xT, cand, cnt, c, n, k, skip, (int)bn, idx, dist2);
     PDGN_CHECK_LAUNCH();

@@ -1010,3 +1010,55 @@ def test_streaming_pull_backward_hubs_groups_batches(dev, b, c, n, m, k):
     scale = age[:, :c].sum(-1) + age[:, c:].sum(-1) + ocpu.group_bwd(np.ascontiguousarray(age[:, c:]), idxe.astype(np.int32), n)
     assert np.all(np.abs(C(ge) - refe) <= 2e-6 * scale + 1e-7)
     assert torch.equal(ge, ops.edge_feat_bwd(G(gee, dev), torch.from_numpy(idxe).to(dev), c))
+
+
+def _generator_like_features(rng, b, c, n):
+    """Non-negative, strongly correlated channels with a common offset (what a ReLU stack hands to get_edge_features)."""
+    z = rng.standard_normal((b, 6, n)).astype(np.float32)
+    w = rng.standard_normal((c, 6)).astype(np.float32)
+    return np.maximum(np.einsum("ck,bkn->bcn", w, z) + 1.0 + 0.05 * rng.standard_normal((b, c, n)).astype(np.float32), 0).astype(np.float32)
+
+
+@pytest.mark.parametrize("name,b,c,n,k", [("randn", 2, 64, 256, 10), ("randn", 1, 256, 1024, 10), ("randn", 3, 32, 128, 10),
+                                          ("relu", 2, 128, 512, 10), ("coherent", 2, 64, 512, 10), ("dups", 2, 32, 256, 10),
+                                          ("randn", 2, 40, 640, 19), ("far", 2, 64, 384, 10), ("nonfinite", 2, 32, 256, 10),
+                                          ("relu", 35, 32, 128, 10)])
+def test_knn_feat_tensor_core_path_bit_exact(dev, name, b, c, n, k):
+    """pdgn_knn_feat_ws on the shapes that take the tcgen05 path (csrc/knn_feat_tc.cu: TF32 Gram tiles in TMEM as a filter, exact
+    FP32 re-rank): indices AND distances equal the oracle's bit for bit -- random, generator-like (correlated, offset), index-
+    coherent, duplicated, far-from-origin and non-finite features -- and equal the FP32 SIMT kernel's."""
+    from oracle import cpu as ocpu
+    from pdgn_b200 import ops
+    from pdgn_b200._lib import lib, check
+    rng = np.random.default_rng(c * 7 + n)
+    if name == "randn":
+        x = rng.standard_normal((b, c, n)).astype(np.float32)
+    elif name == "relu":
+        x = _generator_like_features(rng, b, c, n)
+    elif name == "coherent":
+        t = np.linspace(0, 1, n, dtype=np.float32)
+        x = (np.stack([np.sin((i + 1) * t * 3.0) for i in range(c)])[None] + 1e-3 * rng.standard_normal((b, c, n))).astype(np.float32)
+    elif name == "dups":
+        x = np.repeat(rng.standard_normal((b, c, n // 2)).astype(np.float32), 2, axis=2)
+    elif name == "far":
+        x = (rng.standard_normal((b, c, n)) + 300.0).astype(np.float32)
+    else:
+        x = rng.standard_normal((b, c, n)).astype(np.float32)
+        x[0, 3, 17] = np.nan
+        x[1, 0, 5] = np.inf
+        x[1, 7, 200] = 1e30
+    xt = G(x, dev)
+    idx, d2 = ops.knn_feat(xt, k, skip=1, return_dist=True)
+    ridx, rd2 = ocpu.knn_feat(x, k, skip=1)
+    if name == "nonfinite":
+        # rows that do not involve a non-finite distance must match; the SIMT kernel (whose NaN behaviour the oracle restates)
+        # is the reference for the rest
+        L = lib()
+        i2 = torch.empty_like(idx)
+        e2 = torch.empty_like(d2)
+        check(L.pdgn_knn_feat(xt.data_ptr(), b, c, n, k, 1, i2.data_ptr(), e2.data_ptr(), torch.cuda.current_stream().cuda_stream), "simt")
+        assert torch.equal(idx, i2)
+        assert torch.equal(d2.nan_to_num(nan=-1.0), e2.nan_to_num(nan=-1.0))
+        return
+    np.testing.assert_array_equal(C(idx), ridx)
+    np.testing.assert_array_equal(C(d2), rd2)
