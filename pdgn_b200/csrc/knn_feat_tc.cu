@@ -122,6 +122,9 @@ __device__ __forceinline__ void kf_mma(uint32_t tmem_d, uint64_t adesc, uint64_t
 __device__ __forceinline__ void kf_commit(uint64_t* bar) {
     asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
 }
+__device__ __forceinline__ void mbar_arrive_plain(uint64_t* bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
 __device__ __forceinline__ void kf_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void kf_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void kf_tmem_ld32(uint32_t taddr, float (&v)[32]) {
@@ -161,12 +164,14 @@ __device__ __forceinline__ float kf_flag_threshold(unsigned a16, float ni, float
 
 // ---------------------------------------------------------------- filter
 // grid (n / 128, B), 128 threads.  Dynamic shared memory: A [c/8][32][128 B] | B stage 0, 1 [32][4][128 B] | norms [n] | lists.
+constexpr int TF_T = TF_M + 32;   // 4 epilogue warps (thread = query = TMEM lane) + 1 warp whose lane 0 copies and issues the MMAs
+
 template <int TN>
-__global__ void __launch_bounds__(TF_M, 1) knn_feat_tc_kernel(const float* __restrict__ xc, const float* __restrict__ nrm,
+__global__ void __launch_bounds__(TF_T, 1) knn_feat_tc_kernel(const float* __restrict__ xc, const float* __restrict__ nrm,
                                                             const unsigned* __restrict__ maxn, int c, int n, int kk,
                                                             int* __restrict__ cand, int* __restrict__ cnt, int nst, float* __restrict__ dbg, uint32_t idesc) {
     extern __shared__ __align__(128) unsigned char kf_smem[];
-    __shared__ uint64_t bars[TF_NST], fullb[TF_NST], abar, tileb;   // bars: stage consumed by the tensor core; fullb: stage filled
+    __shared__ uint64_t bars[TF_NST], fullb[TF_NST], abar, tfull[2], tempty[2];   // bars: stage consumed by the tensor core; fullb: stage filled
     __shared__ uint32_t tmem_slot;
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const int bz = blockIdx.y, m0 = blockIdx.x * TF_M;
@@ -185,27 +190,31 @@ __global__ void __launch_bounds__(TF_M, 1) knn_feat_tc_kernel(const float* __res
             mbar_init(&fullb[i], 1);
         }
         mbar_init(&abar, 1);
-        mbar_init(&tileb, 1);        // one phase per accumulator tile: the threads that only meet the tensor core at a tile's end
-        mbar_fence_init();           // must not wait on a ring stage's barrier (two uses per tile would alias its phase parity)
+        for (int i = 0; i < 2; ++i) {
+            mbar_init(&tfull[i], 1);      // accumulator i holds a finished tile (tcgen05.commit of the tile's last K-block)
+            mbar_init(&tempty[i], TF_M);  // accumulator i has been read by all 128 epilogue threads
+        }
+        mbar_fence_init();
     }
     if (warp == 0) {
-        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&tmem_slot)), "r"((uint32_t)TN) : "memory");
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&tmem_slot)), "r"((uint32_t)(2 * TN)) : "memory");
         asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
     }
     __syncthreads();
-    if (tid == 0) {                                                  // A: the query tile's blocks, one bulk copy each
+    const bool issuer = tid == TF_M;                                 // lane 0 of warp 4
+    if (issuer) {                                                    // A: the query tile's blocks, one bulk copy each
         mbar_expect_tx(&abar, (unsigned)nkb * 16384u);
         for (int kb = 0; kb < nkb; ++kb)
             bulk_g2s(a_sm + (size_t)kb * 16384, xcb + ((size_t)blockIdx.x * nkb + kb) * 4096, 16384u, &abar);
     }
-    for (int j = tid; j < n; j += TF_M) nrm_s[j] = nrm[(size_t)bz * n + j];
+    for (int j = tid; j < n; j += TF_T) nrm_s[j] = nrm[(size_t)bz * n + j];
     kf_fence_before();
     __syncthreads();
     kf_fence_after();
     const uint32_t tmem = tmem_slot;
-    const uint32_t trow = tmem + ((uint32_t)(warp * 32) << 16);      // this warp's 32 lanes of the accumulator
+    const uint32_t trow = tmem + ((uint32_t)((warp & 3) * 32) << 16);   // this warp's 32 lanes of the accumulators
 
-    const float ni = nrm_s[m0 + tid];
+    const float ni = nrm_s[m0 + (tid & (TF_M - 1))];
     const float mx = __uint_as_float(maxn[bz]);
     const int ntile = n / TN;
     float mn[TF_SG];
@@ -214,126 +223,132 @@ __global__ void __launch_bounds__(TF_M, 1) knn_feat_tc_kernel(const float* __res
     float fv = 0.f;
     int nl = 0;
     bool over = false;
-    // K-blocks of B, flattened over (pass, tile, K-block): iteration t uses ring stage t % nst.  Thread 0 is the producer AND
-    // the MMA issuer: one 16 KB bulk copy (TMA engine, completes on the stage's "full" mbarrier) per K-block, nst - 1 blocks ahead
-    // of the tensor core; four tcgen05.mma (K = 8 each) per block; tcgen05.commit releases the stage.  The other threads only
-    // meet the tensor core at the end of a tile.  (First version: 16-byte cp.async pieces from a row-major copy by all threads
-    // -- 1.1 us per K-block in the copy path alone, 2.6x slower overall.)
+    // Warp-specialised: thread 128 (lane 0 of warp 4) is the producer AND the MMA issuer -- one 16 KB bulk copy per 128 candidates
+    // and K-block (TMA engine, completes on the stage's "full" mbarrier), up to nst - 1 stages ahead of the tensor core; four
+    // tcgen05.mma (K = 8 each) per K-block; tcgen05.commit releases the stage, and at a tile's last K-block hands the accumulator
+    // to the epilogue.  Two accumulators in TMEM: the K loop of tile g + 1 runs under the epilogue of tile g.  Warps 0-3
+    // (thread = query = TMEM lane) only read accumulators.  Both passes walk the same tile sequence; the threshold of pass B is
+    // ready long before its first tile is (the issuer does not wait for it).
     const int T = 2 * ntile * nkb;
-    int p_kb = 0, p_nt = 0, p_buf = 0, p_round = 0, p_left = T;     // producer cursor (thread 0)
-    auto issue_next = [&]() {
-        mbar_expect_tx(&fullb[p_buf], SB);
+    if (issuer) {
+        int p_kb = 0, p_nt = 0, p_buf = 0, p_round = 0, p_left = T;     // producer cursor
+        auto issue_next = [&]() {
+            mbar_expect_tx(&fullb[p_buf], SB);
 #pragma unroll
-        for (int h = 0; h < NB; ++h)       // consecutive 128-candidate blocks are consecutive 8-point groups of one operand
-            bulk_g2s(b_sm + (size_t)p_buf * SB + (size_t)h * 16384, xcb + ((size_t)(p_nt * NB + h) * nkb + p_kb) * 4096, 16384u, &fullb[p_buf]);
-        if (++p_kb == nkb) {
-            p_kb = 0;
-            if (++p_nt == ntile) p_nt = 0;
-        }
-        if (++p_buf == nst) {
-            p_buf = 0;
-            ++p_round;
-        }
-        --p_left;
-    };
-    if (tid == 0) {
+            for (int h = 0; h < NB; ++h)       // consecutive 128-candidate blocks are consecutive 8-point groups of one operand
+                bulk_g2s(b_sm + (size_t)p_buf * SB + (size_t)h * 16384, xcb + ((size_t)(p_nt * NB + h) * nkb + p_kb) * 4096, 16384u, &fullb[p_buf]);
+            if (++p_kb == nkb) {
+                p_kb = 0;
+                if (++p_nt == ntile) p_nt = 0;
+            }
+            if (++p_buf == nst) {
+                p_buf = 0;
+                ++p_round;
+            }
+            --p_left;
+        };
         for (int t = 0; t < nst - 1; ++t)                            // all but one stage
             if (p_left > 0) issue_next();
         mbar_wait(&abar, 0u);
-    }
-    int buf = 0, round = 0;                                          // consumer: ring stage and how often it has been used
-    int tile_phase = 0;
-    const uint32_t a_s0 = smem_u32(a_sm), b_s0 = smem_u32(b_sm);
-    for (int pass = 0; pass < 2; ++pass) {
-        for (int nt = 0; nt < ntile; ++nt) {
+        int buf = 0, round = 0;                                      // consumer side of the ring
+        const uint32_t a_s0 = smem_u32(a_sm), b_s0 = smem_u32(b_sm);
+        for (int g = 0; g < 2 * ntile; ++g) {
+            const int acc = g & 1;
+            if (g >= 2) mbar_wait(&tempty[acc], (unsigned)(((g >> 1) - 1) & 1));   // the epilogue has drained this accumulator
+            kf_fence_after();
+            const uint32_t tacc = tmem + (uint32_t)(acc * TN);
             for (int kb = 0; kb < nkb; ++kb) {
-                if (tid == 0) {
-                    const uint32_t b_s = b_s0 + (uint32_t)buf * SB, a_s = a_s0 + (uint32_t)kb * 16384u;
-                    mbar_wait(&fullb[buf], (unsigned)(round & 1));   // the block has landed (async proxy: no proxy fence needed)
-                    kf_fence_after();
+                const uint32_t b_s = b_s0 + (uint32_t)buf * SB, a_s = a_s0 + (uint32_t)kb * 16384u;
+                mbar_wait(&fullb[buf], (unsigned)(round & 1));       // the block has landed (async proxy: no proxy fence needed)
+                kf_fence_after();
 #pragma unroll
-                    for (int kc = 0; kc < 4; ++kc)
-                        if (!(idesc & 1u))                           // idesc bit 0 (sparse id, unused): ablation without MMAs
-                            kf_mma(tmem, kf_desc(a_s + (uint32_t)kc * 256u, 128u, 1024u), kf_desc(b_s + (uint32_t)kc * 256u, 128u, 1024u),
-                                   (kb | kc) ? 1u : 0u, idesc);
-                    kf_commit(&bars[buf]);
-                    if (kb == nkb - 1) kf_commit(&tileb);            // the tile's last commit covers every MMA issued before it
-                    // refill the stage the PREVIOUS iteration used, once its MMAs are done: this iteration's MMAs are already
-                    // queued behind them, so the tensor core does not idle while the issuer waits here
-                    if (p_left > 0) {
-                        if (p_round > 0) mbar_wait(&bars[p_buf], (unsigned)((p_round - 1) & 1));
-                        issue_next();
-                    }
+                for (int kc = 0; kc < 4; ++kc)
+                    if (!(idesc & 1u))                               // idesc bit 0 (sparse id, unused): ablation without MMAs
+                        kf_mma(tacc, kf_desc(a_s + (uint32_t)kc * 256u, 128u, 1024u), kf_desc(b_s + (uint32_t)kc * 256u, 128u, 1024u),
+                               (kb | kc) ? 1u : 0u, idesc);
+                kf_commit(&bars[buf]);
+                if (kb == nkb - 1) kf_commit(&tfull[acc]);           // the tile's last commit covers every MMA issued before it
+                // refill the stage the PREVIOUS iteration used, once its MMAs are done: this iteration's MMAs are already queued
+                // behind them, so the tensor core does not idle while the issuer waits here
+                if (p_left > 0) {
+                    if (p_round > 0) mbar_wait(&bars[p_buf], (unsigned)((p_round - 1) & 1));
+                    issue_next();
                 }
                 if (++buf == nst) {
                     buf = 0;
                     ++round;
                 }
             }
-            mbar_wait(&tileb, (unsigned)(tile_phase & 1));
-            ++tile_phase;
-            kf_fence_after();
+        }
+    } else if (tid < TF_M) {
+        int g = 0;
+        for (int pass = 0; pass < 2; ++pass) {
+            for (int nt = 0; nt < ntile; ++nt, ++g) {
+                const int acc = g & 1;
+                mbar_wait(&tfull[acc], (unsigned)((g >> 1) & 1));
+                kf_fence_after();
 #pragma unroll
-            for (int ch = 0; ch < TN / 32; ++ch) {
-                float g[32];
-                kf_tmem_ld32(trow + (uint32_t)(ch * 32), g);
-                if (dbg && pass == 0 && nt == 0 && blockIdx.x == 0 && blockIdx.y == 0) {
+                for (int ch = 0; ch < TN / 32; ++ch) {
+                    float gv[32];
+                    kf_tmem_ld32(trow + (uint32_t)(acc * TN + ch * 32), gv);
+                    if (dbg && pass == 0 && nt == 0 && blockIdx.x == 0 && blockIdx.y == 0) {
 #pragma unroll
-                    for (int u = 0; u < 32; ++u) dbg[tid * TN + ch * 32 + u] = g[u] + 1000.f;
-                }
-                const float4* nj4 = reinterpret_cast<const float4*>(nrm_s + nt * TN + ch * 32);
+                        for (int u = 0; u < 32; ++u) dbg[tid * TN + ch * 32 + u] = gv[u] + 1000.f;
+                    }
+                    const float4* nj4 = reinterpret_cast<const float4*>(nrm_s + nt * TN + ch * 32);
 #pragma unroll
-                for (int q = 0; q < 8; ++q) {
-                    const float4 nj = nj4[q];
-                    const float njv[4] = {nj.x, nj.y, nj.z, nj.w};
+                    for (int q = 0; q < 8; ++q) {
+                        const float4 nj = nj4[q];
+                        const float njv[4] = {nj.x, nj.y, nj.z, nj.w};
 #pragma unroll
-                    for (int u = 0; u < 4; ++u) {
-                        const float t = __fmaf_rn(-2.f, g[4 * q + u], njv[u]);
-                        if (pass == 0) {
-                            mn[(ch & 3) * 32 + 4 * q + u] = fminf(mn[(ch & 3) * 32 + 4 * q + u], t);   // NaN never wins
-                        } else if (__fadd_rn(t, ni) <= fv) {
-                            if (nl < TF_CAP) lst[nl * TF_M + tid] = nt * TN + ch * 32 + 4 * q + u;
-                            else over = true;
-                            nl += nl < TF_CAP ? 1 : 0;
+                        for (int u = 0; u < 4; ++u) {
+                            const float t = __fmaf_rn(-2.f, gv[4 * q + u], njv[u]);
+                            if (pass == 0) {
+                                mn[(ch & 3) * 32 + 4 * q + u] = fminf(mn[(ch & 3) * 32 + 4 * q + u], t);   // NaN never wins
+                            } else if (__fadd_rn(t, ni) <= fv) {
+                                if (nl < TF_CAP) lst[nl * TF_M + tid] = nt * TN + ch * 32 + 4 * q + u;
+                                else over = true;
+                                nl += nl < TF_CAP ? 1 : 0;
+                            }
                         }
                     }
                 }
+                kf_fence_before();
+                mbar_arrive_plain(&tempty[acc]);                     // this thread has read the accumulator
             }
-            kf_fence_before();
-            __syncthreads();                                         // TMEM is read: the next tile may overwrite it
-        }
-        if (pass == 0) {
-            // bound: k'-th smallest of the 64 group minima (group = subgroups g and g + 64), bf16 rounded down, clamped at 0
-            auto grp = [&](int i) -> unsigned {
-                const float h = fmaxf(__fadd_rn(fminf(mn[i], mn[i + 64]), ni), 0.f);
-                return __float_as_uint(h) >> 16;
-            };
-            const unsigned a16 = kq_kth_of_64(grp, kk);
-            if (a16 >= 0x7f80u || !(ni <= 3.402823466e+38f)) {
-                over = true;                                         // fewer than k' finite groups, or a non-finite query
-                fv = -1.f;
-            } else {
-                fv = kf_flag_threshold(a16, ni, mx, c);
-                if (!(fv <= 3.402823466e+38f)) {
-                    over = true;
+            if (pass == 0) {
+                // bound: k'-th smallest of the 64 group minima (group = subgroups g and g + 64), bf16 rounded down, clamped at 0
+                auto grp = [&](int i) -> unsigned {
+                    const float h = fmaxf(__fadd_rn(fminf(mn[i], mn[i + 64]), ni), 0.f);
+                    return __float_as_uint(h) >> 16;
+                };
+                const unsigned a16 = kq_kth_of_64(grp, kk);
+                if (a16 >= 0x7f80u || !(ni <= 3.402823466e+38f)) {
+                    over = true;                                     // fewer than k' finite groups, or a non-finite query
                     fv = -1.f;
+                } else {
+                    fv = kf_flag_threshold(a16, ni, mx, c);
+                    if (!(fv <= 3.402823466e+38f)) {
+                        over = true;
+                        fv = -1.f;
+                    }
                 }
             }
         }
-    }
-    // lists out (flag = -1: the exact kernel recomputes this query)
-    const size_t q = (size_t)bz * n + m0 + tid;
-    if (dbg) {
-        cnt[q] = -1;                                                 // bring-up dump: the Gram tile sits in the list buffer
-    } else if (over || nl < kk) {
-        cnt[q] = -1;
-    } else {
-        cnt[q] = nl;
-        for (int e = 0; e < nl; ++e) cand[q * TF_CAP + e] = lst[e * TF_M + tid];
+        // lists out (flag = -1: the exact kernel recomputes this query)
+        const size_t q = (size_t)bz * n + m0 + tid;
+        if (dbg) {
+            cnt[q] = -1;                                             // bring-up dump: the Gram tile sits in the list buffer
+        } else if (over || nl < kk) {
+            cnt[q] = -1;
+        } else {
+            cnt[q] = nl;
+            for (int e = 0; e < nl; ++e) cand[q * TF_CAP + e] = lst[e * TF_M + tid];
+        }
     }
     kf_fence_before();
     __syncthreads();
-    if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"((uint32_t)TN) : "memory");
+    if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"((uint32_t)(2 * TN)) : "memory");
 }
 
 // ---------------------------------------------------------------- exact re-rank: warp = query, lane = candidate
@@ -451,10 +466,10 @@ int knn_feat_tc_launch(const float* x, int b, int c, int n, int k, int skip, lon
     if (tune_env("PDGN_KNN_FEAT_NOMMA")) idesc |= 1u;
     if (tnsel == 256) {
         PDGN_CUDA(cudaFuncSetAttribute(knn_feat_tc_kernel<256>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        knn_feat_tc_kernel<256><<<dim3(n / TF_M, b), TF_M, smem, st>>>(xc, nrm, maxn, c, n, k + skip, cand, cnt, nst, dbg, idesc);
+        knn_feat_tc_kernel<256><<<dim3(n / TF_M, b), TF_T, smem, st>>>(xc, nrm, maxn, c, n, k + skip, cand, cnt, nst, dbg, idesc);
     } else {
         PDGN_CUDA(cudaFuncSetAttribute(knn_feat_tc_kernel<128>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        knn_feat_tc_kernel<128><<<dim3(n / TF_M, b), TF_M, smem, st>>>(xc, nrm, maxn, c, n, k + skip, cand, cnt, nst, dbg, idesc);
+        knn_feat_tc_kernel<128><<<dim3(n / TF_M, b), TF_T, smem, st>>>(xc, nrm, maxn, c, n, k + skip, cand, cnt, nst, dbg, idesc);
     }
     PDGN_CHECK_LAUNCH();
     knn_feat_rerank_kernel<<<(unsigned)((bn + 7) / 8), 256, 0, st>>>(xT, cand, cnt, c, n, k, skip, (int)bn, idx, dist2);
