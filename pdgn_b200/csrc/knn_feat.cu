@@ -147,7 +147,7 @@ extern "C" int pdgn_knn_feat_ws(const float* x, int b, int c, int n, int k, int 
     if (workspace_bytes < knn_feat_tc_workspace(b, c, n) - 256) return PDGN_ERR_WORKSPACE;
     const int* flags = nullptr;
     const int rc = knn_feat_tc_launch(x, b, c, n, k, skip, reinterpret_cast<long long*>(idx), dist2, workspace, &flags, (cudaStream_t)stream);
-    if (rc != PDGN_OK) return rc;
+    if (rc != PDGN_OK || !flags) return rc;
     const size_t smem = (size_t)(2 * FCK * FB + FB * (FB + 1)) * 4 + (size_t)(k + skip) * FB * 8;
     PDGN_CUDA(cudaFuncSetAttribute(knn_feat_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     dim3 grid((n + FB - 1) / FB, b);

@@ -173,7 +173,7 @@ __global__ void __launch_bounds__(TF_T, 1) knn_feat_tc_kernel(const float* __res
     extern __shared__ __align__(128) unsigned char kf_smem[];
     __shared__ uint64_t bars[TF_NST], fullb[TF_NST], abar, tfull[2], tempty[2];   // bars: stage consumed by the tensor core; fullb: stage filled
     __shared__ uint32_t tmem_slot;
-    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int tid = threadIdx.x, warp = tid >> 5;
     const int bz = blockIdx.y, m0 = blockIdx.x * TF_M;
     const int nkb = (c + TF_KB - 1) / TF_KB;                          // K-blocks (channels zero-padded to a multiple of 32)
     unsigned char* a_sm = kf_smem;                                   // nkb blocks of 16 KB: the CTA's 128 queries, all channels
@@ -352,44 +352,86 @@ __global__ void __launch_bounds__(TF_T, 1) knn_feat_tc_kernel(const float* __res
 }
 
 // ---------------------------------------------------------------- exact re-rank: warp = query, lane = candidate
+// The exact reference chain needs every channel of every candidate row (~14 rows of C floats per query, from the L2-resident
+// xT).  The rows are fetched COALESCED, 64 channels at a time (a half-warp per row), into a padded shared-memory tile, and each
+// lane then walks its own row from there: the first version let every lane read its row straight from global memory (16 bytes
+// per lane and request, 14+ lines per warp request) and ran at 3.5 TB/s of L2 traffic.  The chain stays strictly sequential
+// in c (the accumulator is carried across the 64-channel rounds).
+constexpr int RR_CH = 64;            // channels per round
+constexpr int RR_RS = RR_CH + 4;     // row stride in floats: 272 bytes, conflict-free LDS.128 for 32 lanes on 32 different rows
 __global__ void __launch_bounds__(256) knn_feat_rerank_kernel(const float* __restrict__ xT, const int* __restrict__ cand,
                                                              const int* __restrict__ cnt, int c, int n, int k, int skip, int total,
                                                              long long* __restrict__ idx, float* __restrict__ dist2) {
-    const int q = blockIdx.x * 8 + (threadIdx.x >> 5), lane = threadIdx.x & 31;
+    extern __shared__ __align__(16) float rows_s[];                  // [8 warps][33 rows][RR_RS]
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int q = blockIdx.x * 8 + warp;
     if (q >= total) return;
     const int m = cnt[q];
     if (m < 0) return;                                               // flagged: the exact kernel writes this query
     const int bz = q / n;
     const int j = lane < m ? cand[(size_t)q * TF_CAP + lane] : -1;
-    const float* xi = xT + (size_t)q * c;
-    const float* xj = xT + ((size_t)bz * n + max(j, 0)) * c;
+    float* my = rows_s + (size_t)warp * 33 * RR_RS;
+    const int half = lane >> 4, li = lane & 15;
     float acc = 0.f;
-    if (j < 0) {
-        // idle lane: no loads (the re-rank is bound by the L2 -> SM traffic of the candidate rows)
-    } else if ((c & 15) == 0) {
-        // 64 bytes of each row per step: four independent 16-byte loads in flight per lane (the kernel is bound by the L2 -> SM
-        // traffic of the candidate rows, ~14 KB per query); the chain itself stays strictly sequential in c
-        for (int ch = 0; ch < c; ch += 16) {
-            float4 a[4], b[4];
-#pragma unroll
-            for (int u = 0; u < 4; ++u) {
-                a[u] = __ldg(reinterpret_cast<const float4*>(xi + ch) + u);
-                b[u] = __ldg(reinterpret_cast<const float4*>(xj + ch) + u);
+    for (int c0 = 0; c0 < c; c0 += RR_CH) {
+        const int cw = min(RR_CH, c - c0);                           // multiple of 4 (c % 8 == 0 on this path)
+        // row 0 = the query, row 1 + l = lane l's candidate; two rows per step, 16 lanes x 16 bytes each
+        for (int r0 = 0; r0 <= m; r0 += 2) {
+            const int row = r0 + half;
+            const int jj = __shfl_sync(kFull, j, max(row - 1, 0));
+            if (row <= m && li * 4 < cw) {
+                const float* src = row == 0 ? xT + (size_t)q * c : xT + ((size_t)bz * n + jj) * c;
+                *reinterpret_cast<float4*>(my + row * RR_RS + li * 4) = __ldg(reinterpret_cast<const float4*>(src + c0) + li);
             }
-#pragma unroll
-            for (int u = 0; u < 4; ++u) {
-                float d = __fsub_rn(a[u].x, b[u].x);
+        }
+        __syncwarp();
+        if (j >= 0) {
+            const float4* a4 = reinterpret_cast<const float4*>(my);
+            const float4* b4 = reinterpret_cast<const float4*>(my + (1 + lane) * RR_RS);
+#pragma unroll 4
+            for (int u = 0; u < (cw >> 2); ++u) {
+                const float4 a = a4[u], b = b4[u];
+                float d = __fsub_rn(a.x, b.x);
                 acc = __fmaf_rn(d, d, acc);
-                d = __fsub_rn(a[u].y, b[u].y);
+                d = __fsub_rn(a.y, b.y);
                 acc = __fmaf_rn(d, d, acc);
-                d = __fsub_rn(a[u].z, b[u].z);
+                d = __fsub_rn(a.z, b.z);
                 acc = __fmaf_rn(d, d, acc);
-                d = __fsub_rn(a[u].w, b[u].w);
+                d = __fsub_rn(a.w, b.w);
                 acc = __fmaf_rn(d, d, acc);
             }
         }
-    } else if ((c & 3) == 0) {
-        for (int ch = 0; ch < c; ch += 4) {
+        __syncwarp();
+    }
+    const unsigned long long key = j >= 0 ? (((unsigned long long)__float_as_uint(acc) << 32) | (unsigned)j) : ~0ull;
+    int rank = 0;
+#pragma unroll
+    for (int o = 0; o < 32; ++o) rank += __shfl_sync(kFull, key, o) < key ? 1 : 0;
+    if (j >= 0 && rank >= skip && rank < skip + k) {
+        idx[(size_t)q * k + rank - skip] = j;
+        if (dist2) dist2[(size_t)q * k + rank - skip] = acc;
+    }
+}
+
+// ---------------------------------------------------------------- flagged queries: exact brute force, warp = query
+// Queries the filter could not bound (list overflow, duplicates / clusters, non-finite values) are few; a warp computes all n
+// reference distances of its query once into shared memory and selects ranks skip..skip+k-1 by repeated minimum search over the
+// (d2, index) keys.  Non-finite distances are never selected and missing ranks read index 0 / +inf, exactly like
+// knn_feat_kernel's insertion list (knn_feat.cu), whose per-CTA cost (64 queries at a time) made one flagged query a 0.3 ms tail.
+__global__ void __launch_bounds__(256) knn_feat_brute_kernel(const float* __restrict__ xT, const int* __restrict__ cnt, int c, int n,
+                                                            int k, int skip, int total, long long* __restrict__ idx,
+                                                            float* __restrict__ dist2) {
+    extern __shared__ __align__(16) float bd_s[];                    // [8 warps][n]
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int q = blockIdx.x * 8 + warp;
+    if (q >= total || cnt[q] >= 0) return;
+    const int bz = q / n;
+    float* dsm = bd_s + (size_t)warp * n;
+    const float* xi = xT + (size_t)q * c;
+    for (int t = lane; t < n; t += 32) {
+        const float* xj = xT + ((size_t)bz * n + t) * c;
+        float acc = 0.f;
+        for (int ch = 0; ch < c; ch += 4) {                          // c % 8 == 0 on this path
             const float4 a = __ldg(reinterpret_cast<const float4*>(xi + ch)), b = __ldg(reinterpret_cast<const float4*>(xj + ch));
             float d = __fsub_rn(a.x, b.x);
             acc = __fmaf_rn(d, d, acc);
@@ -400,19 +442,34 @@ __global__ void __launch_bounds__(256) knn_feat_rerank_kernel(const float* __res
             d = __fsub_rn(a.w, b.w);
             acc = __fmaf_rn(d, d, acc);
         }
-    } else {
-        for (int ch = 0; ch < c; ++ch) {
-            const float d = __fsub_rn(__ldg(xi + ch), __ldg(xj + ch));
-            acc = __fmaf_rn(d, d, acc);
-        }
+        dsm[t] = acc;
     }
-    const unsigned long long key = j >= 0 ? (((unsigned long long)__float_as_uint(acc) << 32) | (unsigned)j) : ~0ull;
-    int rank = 0;
+    __syncwarp();
+    unsigned long long last = 0;
+    for (int e = 0; e < k + skip; ++e) {
+        unsigned long long best = ~0ull;
+        for (int t = lane; t < n; t += 32) {
+            const float d = dsm[t];
+            const unsigned long long key = ((unsigned long long)__float_as_uint(d) << 32) | (unsigned)t;
+            if (d < kInf && (e == 0 || key > last) && key < best) best = key;   // NaN / +inf are never selected
+        }
 #pragma unroll
-    for (int o = 0; o < 32; ++o) rank += __shfl_sync(kFull, key, o) < key ? 1 : 0;
-    if (j >= 0 && rank >= skip && rank < skip + k) {
-        idx[(size_t)q * k + rank - skip] = j;
-        if (dist2) dist2[(size_t)q * k + rank - skip] = acc;
+        for (int o = 16; o > 0; o >>= 1) {
+            const unsigned long long other = __shfl_xor_sync(kFull, best, o);
+            best = other < best ? other : best;
+        }
+        if (best == ~0ull) {                                         // fewer finite candidates than ranks
+            for (int f = max(e, skip) + lane; f < k + skip; f += 32) {
+                idx[(size_t)q * k + f - skip] = 0;
+                if (dist2) dist2[(size_t)q * k + f - skip] = kInf;
+            }
+            break;
+        }
+        if (lane == 0 && e >= skip) {
+            idx[(size_t)q * k + e - skip] = (long long)(unsigned)best;
+            if (dist2) dist2[(size_t)q * k + e - skip] = __uint_as_float((unsigned)(best >> 32));
+        }
+        last = best;
     }
 }
 
@@ -472,9 +529,15 @@ int knn_feat_tc_launch(const float* x, int b, int c, int n, int k, int skip, lon
         knn_feat_tc_kernel<128><<<dim3(n / TF_M, b), TF_T, smem, st>>>(xc, nrm, maxn, c, n, k + skip, cand, cnt, nst, dbg, idesc);
     }
     PDGN_CHECK_LAUNCH();
-    knn_feat_rerank_kernel<<<(unsigned)((bn + 7) / 8), 256, 0, st>>>(xT, cand, cnt, c, n, k, skip, (int)bn, idx, dist2);
+    const size_t rr_smem = (size_t)8 * 33 * RR_RS * 4;
+    PDGN_CUDA(cudaFuncSetAttribute(knn_feat_rerank_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)rr_smem));
+    knn_feat_rerank_kernel<<<(unsigned)((bn + 7) / 8), 256, rr_smem, st>>>(xT, cand, cnt, c, n, k, skip, (int)bn, idx, dist2);
     PDGN_CHECK_LAUNCH();
-    *flags = cnt;
+    const size_t bf_smem = (size_t)8 * n * 4;
+    PDGN_CUDA(cudaFuncSetAttribute(knn_feat_brute_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bf_smem));
+    knn_feat_brute_kernel<<<(unsigned)((bn + 7) / 8), 256, bf_smem, st>>>(xT, cnt, c, n, k, skip, (int)bn, idx, dist2);
+    PDGN_CHECK_LAUNCH();
+    *flags = nullptr;                                                // nothing left for the caller to recompute
     return PDGN_OK;
 }
 
