@@ -660,7 +660,17 @@ def bench_cfg3(dev):
         # the kNN kernel of the stage alone: exact FP32 direct distances, 2C FMA-pipe instructions per (query, candidate) pair
         from pdgn_b200 import ops
         kms = _ev_ms(lambda: ops.knn_feat(x, 10, skip=1))
-        feat_knn["C%d_N%d" % (c, n)] = {"ms": kms, "fp32_issue_frac": B * n * n * 2.0 * c / (kms * 1e-3) / (148 * 128 * 1.965e9)}
+        # the same op on the FP32 SIMT kernel (csrc/knn_feat.cu), which the tensor-core path (csrc/knn_feat_tc.cu: tcgen05 TF32
+        # Gram filter + exact FP32 re-rank, identical indices) replaced for these shapes
+        from pdgn_b200._lib import lib as _lib_
+        _L = _lib_()
+        _idx = torch.empty((B, n, 10), dtype=torch.int64, device=dev)
+        _st = torch.cuda.current_stream().cuda_stream
+        sms = _ev_ms(lambda: _L.pdgn_knn_feat(x.data_ptr(), B, c, n, 10, 1, _idx.data_ptr(), None, _st))
+        feat_knn["C%d_N%d" % (c, n)] = {"ms": kms, "impl": "tcgen05 tf32 filter + exact fp32 re-rank", "simt_kernel_ms": sms,
+                                        "speedup_over_simt": sms / kms,
+                                        "fp32_issue_frac": B * n * n * 2.0 * c / (kms * 1e-3) / (148 * 128 * 1.965e9),
+                                        "fp32_issue_frac_note": "direct-form work (2 FP32 instr per pair and channel) / time / FP32 issue peak; > 1 is possible: the pairwise work runs on the tensor cores"}
     res["edge_feature_stage_fwd_bwd_ms"] = stages
     res["feature_knn"] = feat_knn
     try:

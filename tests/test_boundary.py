@@ -29,7 +29,7 @@ def test_header_declares_the_expected_entry_points():
     for name in ["pdgn_knn_xyz", "pdgn_nn3", "pdgn_group_fwd", "pdgn_group_bwd", "pdgn_interp_fwd", "pdgn_interp_bwd",
                  "pdgn_chamfer_min", "pdgn_chamfer_bwd", "pdgn_cd_allpairs", "pdgn_cd_allpairs_workspace",
                  "pdgn_cd_allpairs_host", "pdgn_knn_feat", "pdgn_edge_feat_fwd", "pdgn_edge_feat_bwd", "pdgn_group_bwd_ws",
-                 "pdgn_interp_bwd_ws", "pdgn_edge_feat_bwd_ws"]:
+                 "pdgn_interp_bwd_ws", "pdgn_edge_feat_bwd_ws", "pdgn_knn_feat_ws", "pdgn_knn_feat_workspace"]:
         assert name in syms
 
 
