@@ -1062,3 +1062,37 @@ def test_knn_feat_tensor_core_path_bit_exact(dev, name, b, c, n, k):
         return
     np.testing.assert_array_equal(C(idx), ridx)
     np.testing.assert_array_equal(C(d2), rd2)
+
+
+@pytest.mark.parametrize("case", ["n4096", "c8_n4096", "identical", "constant_channel", "skip0_k20", "two_clusters"])
+def test_knn_feat_tensor_core_path_edge_cases(dev, case):
+    """Shapes and inputs at the limits of the tensor-core path: the largest cloud (ring depth falls to the shared-memory budget),
+    the smallest channel count, all-identical points and exact duplicates by the hundred (every query is flagged and takes the
+    exact brute force), a channel without variance, skip = 0 with k = 20 (the largest k' the path takes), two tight clusters
+    (the bound of most queries is set inside their own cluster)."""
+    from oracle import cpu as ocpu
+    from pdgn_b200 import ops
+    rng = np.random.default_rng(11)
+    k, skip = 10, 1
+    if case == "n4096":
+        x = rng.standard_normal((1, 64, 4096)).astype(np.float32)
+    elif case == "c8_n4096":
+        x = rng.standard_normal((2, 8, 4096)).astype(np.float32)
+        k = 4
+    elif case == "identical":
+        x = np.ones((2, 32, 256), dtype=np.float32) * 0.37
+        x[1, :, 100:] += rng.standard_normal((32, 1)).astype(np.float32)      # second element: two groups of identical points
+    elif case == "constant_channel":
+        x = rng.standard_normal((2, 64, 256)).astype(np.float32)
+        x[:, 5] = 3.25
+        x[:, 17] = 0.0
+    elif case == "skip0_k20":
+        x = rng.standard_normal((2, 64, 512)).astype(np.float32)
+        k, skip = 20, 0
+    else:
+        x = (0.01 * rng.standard_normal((2, 32, 384))).astype(np.float32)
+        x[:, :, 192:] += 5.0
+    idx, d2 = ops.knn_feat(G(x, dev), k, skip=skip, return_dist=True)
+    ridx, rd2 = ocpu.knn_feat(x, k, skip=skip)
+    np.testing.assert_array_equal(C(idx), ridx)
+    np.testing.assert_array_equal(C(d2), rd2)
