@@ -43,7 +43,7 @@ const char *pdgn_error_string(int code);
  * xyz [b,n,3] references, new_xyz [b,m,3] queries -> idx int32 [b,m,k], dist2 f32 [b,m,k] (may be NULL).
  * Result order: ascending (d2, index) with d2 = fma(dz,dz, fma(dx,dx, dy*dy)) -- bit-identical to the
  * reference kernel as compiled by nvcc 12.9 -O2.  n < k: trailing idx 0 / dist2 +inf.  NaN or +inf
- * distances are never selected.  1 <= k <= 128. */
+ * distances are never selected.  1 <= k <= 200 (the reference's own limit: best_dist[200], knnquery_cuda_kernel.cu:21-22). */
 int pdgn_knn_xyz(const float *xyz, const float *new_xyz, int b, int n, int m, int k, int *idx, float *dist2,
                  void *stream);
 

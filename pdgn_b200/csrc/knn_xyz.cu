@@ -22,7 +22,7 @@
 //           idx[rank].  Warp-uniform control flow throughout.
 //   A survivor overflow (adversarial ties / clustering / fewer than k finite candidates) sends that one query to
 //   a warp-cooperative exact selection (k rounds of a min-search over all candidates), so the result is always exact.
-// Generic path (knn_generic_kernel): any k <= 128, any n; threshold-guarded insertion into a shared-memory list.
+// Generic path (knn_generic_kernel): any k <= 200, any n; threshold-guarded insertion into a shared-memory list.
 #include <cstdlib>
 #include "common.cuh"
 #include "multi.cuh"
@@ -627,7 +627,7 @@ using namespace pdgn;
 extern "C" int pdgn_knn_xyz(const float* xyz, const float* new_xyz, int b, int n, int m, int k, int* idx, float* dist2, void* stream) {
     PDGN_RANGE("pdgn_knn_xyz");
     if (b < 0 || n < 0 || m < 0 || k < 1) return PDGN_ERR_BAD_ARG;
-    if (k > 128 || b > 65535) return PDGN_ERR_UNSUPPORTED;
+    if (k > 200 || b > 65535) return PDGN_ERR_UNSUPPORTED;   // the reference keeps best_dist[200] (knnquery_cuda_kernel.cu:21-22)
     if (b == 0 || m == 0) return PDGN_OK;  // empty query set: nothing to write (pointers may be null)
     if (!new_xyz || !idx || (!xyz && n > 0)) return PDGN_ERR_BAD_ARG;
     // n == 0 falls through to the generic kernel, which leaves the reference's initial values (idx 0, dist +inf)

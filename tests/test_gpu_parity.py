@@ -38,6 +38,8 @@ KNN_CASES = [
     ("S-k32-G64", clouds_sphere, 1, 4100, 513, 32),
     ("T-k32", clouds_ties, 1, 700, None, 32),
     ("U-k50-generic", clouds_uniform, 1, 333, 100, 50),
+    ("U-k200-reference-limit", clouds_uniform, 2, 700, 150, 200),      # best_dist[200] is the reference kernel's own bound
+    ("T-k129-ties-generic", clouds_ties, 1, 400, 90, 129),
     ("U-small-n-generic", clouds_uniform, 2, 40, 40, 20),
     ("U-n-lt-k", clouds_uniform, 2, 5, 9, 8),
     ("U-train-256x2048", clouds_uniform, 3, 2048, 256, 20),
