@@ -7,24 +7,28 @@
 // and channel) for the shapes below.  Same contract as knn_feat.cu: d2(i,j) = ONE fma chain over c = 0..C-1 of
 // (x[c,i] - x[c,j])^2, total order (d2, index), ranks skip..skip+k-1; bit-exact against oracle_knn_feat.
 //
-//   prep    (2 small kernels)  channel means; centred copy xc = tf32_rn(x - mean) [B,C,N] (distances are shift invariant, the
-//           norms shrink to the spread of the features, and values that ARE tf32 make the tensor core's operand truncation a
-//           no-op); squared norms of the centred rows; xT = x transposed [B,N,C] for the re-rank.
-//   filter  (knn_feat_tc_kernel)  CTA = 128 queries (= the 128 TMEM lanes) x all candidates, 128 at a time.  Operands are
-//           staged by 16-byte cp.async into the canonical MN-major, no-swizzle UMMA layout (core matrix = 8 channels x 4
-//           points); one thread issues tcgen05.mma.kind::tf32 (M = 128, N = 128, K = 8) for every 8 channels, the Gram tile
-//           accumulates in TMEM and the 128 threads read their own row back with tcgen05.ld.  Thread = query:
+//   prep    (kf_mean_kernel, kf_prep_kernel)  channel means; the centred copy xc = tf32_rn(x - mean), PRE-TILED in the tensor
+//           core's operand order (16 KB blocks of 128 points x 32 channels, K-major rows of 128 bytes, SWIZZLE_128B) so that an
+//           operand stage is one contiguous bulk copy; squared norms of the rounded rows; xT = x transposed [B,N,C] for the
+//           re-rank.  Distances are shift invariant: centring shrinks the norms to the spread of the features, and values that
+//           ARE tf32 make the tensor core's operand truncation a no-op.
+//   filter  (knn_feat_tc_kernel<128|256>)  CTA = 128 queries (= the 128 TMEM lanes) x all candidates; 5 warps.  Thread 128
+//           copies (cp.async.bulk into a ring of stages, "full" mbarriers) and issues tcgen05.mma.kind::tf32 (M = 128,
+//           N = 128 or 256, K = 8) for every 8 channels; tcgen05.commit releases the stage and hands a finished accumulator to
+//           the epilogue; two accumulators in TMEM, so the K loop of the next tile runs under the epilogue of this one.  Warps
+//           0-3 (thread = query) read their row back with tcgen05.ld:
 //             pass A  h = |xi|^2 + |xj|^2 - 2 G as running minima of 128 STRIDED subgroups (candidate j -> subgroup j mod 128)
 //                     in registers; bound = k'-th smallest of the 64 group minima (selnet.cuh, the xyz kernel's network);
 //             pass B  the Gram tiles are computed AGAIN (the tensor-core time is small next to the operand traffic) and every
 //                     candidate with h <= F is appended to the query's list (<= 32 entries).
-//           The margins are rigorous (kf_bounds): U bounds the k'-th smallest REFERENCE distance from above and every
+//           The margins are rigorous (kf_flag_threshold): U bounds the k'-th smallest REFERENCE distance from above and every
 //           candidate with d_ref <= U has h <= F.  Nothing depends on the tensor core's internal summation order beyond a
 //           generous absolute error term.
-//   rank    (knn_feat_rerank_kernel)  warp = query, lane = candidate: the exact reference chain from xT (16-byte loads), rank
-//           by counting over the (d2, index) keys, ranks skip..skip+k-1 stored.
+//   rank    (knn_feat_rerank_kernel)  warp = query, lane = candidate: the exact reference chain over rows fetched coalesced into
+//           shared memory, rank by counting over the (d2, index) keys, ranks skip..skip+k-1 stored.
 //   Queries whose list overflowed, or that saw fewer than k' finite group minima (duplicates, clusters, NaN), are flagged and
-//   recomputed by knn_feat.cu's exact kernel, which skips every CTA without a flagged query.
+//   recomputed by knn_feat_brute_kernel (warp = query, all n exact distances, repeated minimum search).
+// Bring-up history and measurements: profiles/r02_knn_feat_tc.txt.
 #include "common.cuh"
 #include "selnet.cuh"
 
@@ -62,9 +66,11 @@ __global__ void __launch_bounds__(256) kf_prep_kernel(const float* __restrict__ 
     __shared__ float part[8][32];
     const int bz = blockIdx.y, n0 = blockIdx.x * 32, tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
     const float* xb = x + (size_t)bz * c * n;
-    // centred rows, PRE-TILED in the tensor core's operand order: one 16 KB block per (128 points, 32 channels), laid out
-    // [8-point group 16][4-channel chunk 8][point 8][4 floats] = the canonical K-major, no-swizzle UMMA core-matrix order, so
-    // a whole operand stage is ONE contiguous bulk copy.  Channels are padded with zeros to a multiple of 32.
+    // centred rows, PRE-TILED in the tensor core's operand order: one 16 KB block per (128 points, 32 channels) = 128 rows of
+    // 128 bytes (K-major), the 16-byte chunks of a row XOR-swizzled with (row % 8) = the canonical SWIZZLE_128B UMMA layout
+    // (8-row atoms of 1024 bytes), so a whole operand stage is ONE contiguous bulk copy.  (The no-swizzle core-matrix order
+    // [8-point group][4-channel chunk][point][4 floats] was the first working version and runs at the same speed.)  Channels
+    // are padded with zeros to a multiple of 32.
     const int nkb = (c + 31) >> 5;
     float* xcb = xc + (size_t)bz * n * nkb * 32;
     float* xtb = xT + (size_t)bz * n * c;
@@ -86,7 +92,7 @@ __global__ void __launch_bounds__(256) kf_prep_kernel(const float* __restrict__ 
             if (n0 + r < n) {
                 if (c0 + tx < c) xtb[(size_t)(n0 + r) * c + c0 + tx] = tile[tx][r];
                 const int pnt = n0 + r;
-                xcb[((size_t)(pnt >> 7) * nkb + (c0 >> 5)) * 4096 + ((pnt & 127) >> 3) * 256 + (tx >> 2) * 32 + (pnt & 7) * 4 + (tx & 3)] = tilec[tx][r];
+                xcb[((size_t)(pnt >> 7) * nkb + (c0 >> 5)) * 4096 + (pnt & 127) * 32 + (((tx >> 2) ^ (pnt & 7)) << 2) + (tx & 3)] = tilec[tx][r];
             }
         __syncthreads();
     }
@@ -103,10 +109,13 @@ __global__ void __launch_bounds__(256) kf_prep_kernel(const float* __restrict__ 
 
 // ---------------------------------------------------------------- tcgen05 helpers
 __device__ __forceinline__ uint64_t kf_desc(uint32_t saddr, uint32_t lbo_bytes, uint32_t sbo_bytes) {
-    // UMMA shared-memory descriptor, K-major, no swizzle (canonical layout ((8,m),(4,2)):((4,SBO),(1,LBO)) in tf32 elements):
-    // a core matrix is 8 points x 16 bytes (4 channels) = 128 contiguous bytes; LBO = bytes between the two core matrices that
-    // make up K = 8, SBO = bytes between 8-point groups.  Offsets in 16-byte units, descriptor version 1 (sm_100).
-    return (uint64_t)((saddr & 0x3ffffu) >> 4) | ((uint64_t)(lbo_bytes >> 4) << 16) | ((uint64_t)(sbo_bytes >> 4) << 32) | (1ull << 46);
+    // UMMA shared-memory descriptor, K-major, SWIZZLE_128B (canonical layout ((8,m),(4,2)):((32,SBO),(1,4)) in tf32 elements
+    // under Swizzle<3,4,3>): a row is 128 contiguous bytes (32 channels), 8 rows form a 1024-byte atom whose 16-byte chunks are
+    // XORed with the row number, SBO = bytes between atoms; the leading offset is unused for a swizzled K-major operand.
+    // A K = 8 step inside the atom is addressed by advancing the start address by 32 bytes.  Offsets in 16-byte units,
+    // descriptor version 1 (sm_100).  The tile base must be 1024-byte aligned (base offset 0).
+    return (uint64_t)((saddr & 0x3ffffu) >> 4) | ((uint64_t)(lbo_bytes >> 4) << 16) | ((uint64_t)(sbo_bytes >> 4) << 32) | (1ull << 46) |
+           (2ull << 61);   // layout type 2 = SWIZZLE_128B
 }
 // instruction descriptor: D = F32, A = B = TF32, both K-major, N = tn, M = 128
 constexpr uint32_t kf_idesc(int tn) { return (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(tn >> 3) << 17) | ((uint32_t)(TF_M >> 4) << 24); }
@@ -170,7 +179,7 @@ template <int TN>
 __global__ void __launch_bounds__(TF_T, 1) knn_feat_tc_kernel(const float* __restrict__ xc, const float* __restrict__ nrm,
                                                             const unsigned* __restrict__ maxn, int c, int n, int kk,
                                                             int* __restrict__ cand, int* __restrict__ cnt, int nst, float* __restrict__ dbg, uint32_t idesc) {
-    extern __shared__ __align__(128) unsigned char kf_smem[];
+    extern __shared__ __align__(1024) unsigned char kf_smem[];
     __shared__ uint64_t bars[TF_NST], fullb[TF_NST], abar, tfull[2], tempty[2];   // bars: stage consumed by the tensor core; fullb: stage filled
     __shared__ uint32_t tmem_slot;
     const int tid = threadIdx.x, warp = tid >> 5;
@@ -264,7 +273,7 @@ __global__ void __launch_bounds__(TF_T, 1) knn_feat_tc_kernel(const float* __res
 #pragma unroll
                 for (int kc = 0; kc < 4; ++kc)
                     if (!(idesc & 1u))                               // idesc bit 0 (sparse id, unused): ablation without MMAs
-                        kf_mma(tacc, kf_desc(a_s + (uint32_t)kc * 256u, 128u, 1024u), kf_desc(b_s + (uint32_t)kc * 256u, 128u, 1024u),
+                        kf_mma(tacc, kf_desc(a_s + (uint32_t)kc * 32u, 16u, 1024u), kf_desc(b_s + (uint32_t)kc * 32u, 16u, 1024u),
                                (kb | kc) ? 1u : 0u, idesc);
                 kf_commit(&bars[buf]);
                 if (kb == nkb - 1) kf_commit(&tfull[acc]);           // the tile's last commit covers every MMA issued before it
