@@ -229,7 +229,7 @@ __global__ void __launch_bounds__(TF_T, 1) knn_feat_tc_kernel(const float* __res
     float mn[TF_SG];
 #pragma unroll
     for (int i = 0; i < TF_SG; ++i) mn[i] = kInf;
-    float fv = 0.f;
+    float fv = 0.f, ft = -kInf;
     int nl = 0;
     bool over = false;
     // Warp-specialised: thread 128 (lane 0 of warp 4) is the producer AND the MMA issuer -- one 16 KB bulk copy per 128 candidates
@@ -297,7 +297,7 @@ __global__ void __launch_bounds__(TF_T, 1) knn_feat_tc_kernel(const float* __res
                 mbar_wait(&tfull[acc], (unsigned)((g >> 1) & 1));
                 kf_fence_after();
 #pragma unroll
-                for (int ch = 0; ch < TN / 32; ++ch) {
+                for (int ch = 0; ch < ((idesc & 2u) ? 0 : TN / 32); ++ch) {   // idesc bit 1 (unused sparse id): ablation without epilogue
                     float gv[32];
                     kf_tmem_ld32(trow + (uint32_t)(acc * TN + ch * 32), gv);
                     if (dbg && pass == 0 && nt == 0 && blockIdx.x == 0 && blockIdx.y == 0) {
@@ -314,7 +314,7 @@ __global__ void __launch_bounds__(TF_T, 1) knn_feat_tc_kernel(const float* __res
                             const float t = __fmaf_rn(-2.f, gv[4 * q + u], njv[u]);
                             if (pass == 0) {
                                 mn[(ch & 3) * 32 + 4 * q + u] = fminf(mn[(ch & 3) * 32 + 4 * q + u], t);   // NaN never wins
-                            } else if (__fadd_rn(t, ni) <= fv) {
+                            } else if (t <= ft) {                    // one compare per candidate: ft >= every t with fl(t + ni) <= fv
                                 if (nl < TF_CAP) lst[nl * TF_M + tid] = nt * TN + ch * 32 + 4 * q + u;
                                 else over = true;
                                 nl += nl < TF_CAP ? 1 : 0;
@@ -340,6 +340,11 @@ __global__ void __launch_bounds__(TF_T, 1) knn_feat_tc_kernel(const float* __res
                     if (!(fv <= 3.402823466e+38f)) {
                         over = true;
                         fv = -1.f;
+                    } else {
+                        // pass B compares t = fl(nj - 2G) itself: fl(t + ni) <= fv implies t + ni <= fv (1 + 2^-23), hence
+                        // t <= ft := ru(ru(fv (1 + 2^-22)) - ni) + one more ulp of slack
+                        const float up = __fmul_ru(fv, 1.f + 2.3841858e-7f);
+                        ft = __fadd_ru(__fsub_ru(up, ni), __fmul_ru(fabsf(up) + fabsf(ni), 1.1920929e-7f));
                     }
                 }
             }
@@ -530,6 +535,7 @@ int knn_feat_tc_launch(const float* x, int b, int c, int n, int k, int skip, lon
     float* dbg = tune_env("PDGN_KNN_FEAT_DBG") ? reinterpret_cast<float*>(cand) : nullptr;
     uint32_t idesc = kf_idesc(tnsel);
     if (tune_env("PDGN_KNN_FEAT_NOMMA")) idesc |= 1u;
+    if (tune_env("PDGN_KNN_FEAT_NOEPI")) idesc |= 2u;
     if (tnsel == 256) {
         PDGN_CUDA(cudaFuncSetAttribute(knn_feat_tc_kernel<256>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         knn_feat_tc_kernel<256><<<dim3(n / TF_M, b), TF_T, smem, st>>>(xc, nrm, maxn, c, n, k + skip, cand, cnt, nst, dbg, idesc);
