@@ -173,7 +173,8 @@ __device__ __forceinline__ float kf_flag_threshold(unsigned a16, float ni, float
 
 // ---------------------------------------------------------------- filter
 // grid (n / 128, B), 128 threads.  Dynamic shared memory: A [c/8][32][128 B] | B stage 0, 1 [32][4][128 B] | norms [n] | lists.
-constexpr int TF_T = TF_M + 32;   // 4 epilogue warps (thread = query = TMEM lane) + 1 warp whose lane 0 copies and issues the MMAs
+constexpr int TF_E = 2 * TF_M;     // 8 epilogue warps: two threads per query (= TMEM lane), each takes every other 32-column chunk
+constexpr int TF_T = TF_E + 32;    // + 1 warp whose lane 0 copies and issues the MMAs
 
 template <int TN>
 __global__ void __launch_bounds__(TF_T, 1) knn_feat_tc_kernel(const float* __restrict__ xc, const float* __restrict__ nrm,
@@ -201,7 +202,7 @@ __global__ void __launch_bounds__(TF_T, 1) knn_feat_tc_kernel(const float* __res
         mbar_init(&abar, 1);
         for (int i = 0; i < 2; ++i) {
             mbar_init(&tfull[i], 1);      // accumulator i holds a finished tile (tcgen05.commit of the tile's last K-block)
-            mbar_init(&tempty[i], TF_M);  // accumulator i has been read by all 128 epilogue threads
+            mbar_init(&tempty[i], TF_E);  // accumulator i has been read by all 256 epilogue threads
         }
         mbar_fence_init();
     }
@@ -210,7 +211,7 @@ __global__ void __launch_bounds__(TF_T, 1) knn_feat_tc_kernel(const float* __res
         asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
     }
     __syncthreads();
-    const bool issuer = tid == TF_M;                                 // lane 0 of warp 4
+    const bool issuer = tid == TF_E;                                 // lane 0 of warp 8
     if (issuer) {                                                    // A: the query tile's blocks, one bulk copy each
         mbar_expect_tx(&abar, (unsigned)nkb * 16384u);
         for (int kb = 0; kb < nkb; ++kb)
@@ -224,13 +225,17 @@ __global__ void __launch_bounds__(TF_T, 1) knn_feat_tc_kernel(const float* __res
     const uint32_t trow = tmem + ((uint32_t)((warp & 3) * 32) << 16);   // this warp's 32 lanes of the accumulators
 
     const float ni = nrm_s[m0 + (tid & (TF_M - 1))];
+    unsigned short* exch = reinterpret_cast<unsigned short*>(lst);   // [2][32][128] group minima between the passes (the lists are idle)
+    int* cnt_s = lst + TF_CAP * TF_M;                                // [128] list lengths, [128] overflow flags
     const float mx = __uint_as_float(maxn[bz]);
     const int ntile = n / TN;
-    float mn[TF_SG];
+    // Epilogue thread (row, half): half h takes the 32-column chunks ch with ch % 2 == h, i.e. the subgroups [32h, 32h + 32) and
+    // [64 + 32h, 96 + 32h) -- the two threads of a query own DISJOINT groups (i, i + 64), 32 each.
+    const int row = tid & (TF_M - 1), half = (tid >> 7) & 1;
+    float mn[TF_SG / 2];
 #pragma unroll
-    for (int i = 0; i < TF_SG; ++i) mn[i] = kInf;
+    for (int i = 0; i < TF_SG / 2; ++i) mn[i] = kInf;
     float fv = 0.f, ft = -kInf;
-    int nl = 0;
     bool over = false;
     // Warp-specialised: thread 128 (lane 0 of warp 4) is the producer AND the MMA issuer -- one 16 KB bulk copy per 128 candidates
     // and K-block (TMA engine, completes on the stage's "full" mbarrier), up to nst - 1 stages ahead of the tensor core; four
@@ -289,7 +294,11 @@ __global__ void __launch_bounds__(TF_T, 1) knn_feat_tc_kernel(const float* __res
                 }
             }
         }
-    } else if (tid < TF_M) {
+    } else if (tid < TF_E) {
+        if (half == 0) {
+            cnt_s[row] = 0;
+            cnt_s[TF_M + row] = 0;
+        }
         int g = 0;
         for (int pass = 0; pass < 2; ++pass) {
             for (int nt = 0; nt < ntile; ++nt, ++g) {
@@ -297,12 +306,13 @@ __global__ void __launch_bounds__(TF_T, 1) knn_feat_tc_kernel(const float* __res
                 mbar_wait(&tfull[acc], (unsigned)((g >> 1) & 1));
                 kf_fence_after();
 #pragma unroll
-                for (int ch = 0; ch < ((idesc & 2u) ? 0 : TN / 32); ++ch) {   // idesc bit 1 (unused sparse id): ablation without epilogue
+                for (int cq = 0; cq < ((idesc & 2u) ? 0 : TN / 64); ++cq) {   // idesc bit 1 (unused sparse id): ablation without epilogue
+                    const int ch = 2 * cq + half;                    // this thread's chunk of the pair
                     float gv[32];
                     kf_tmem_ld32(trow + (uint32_t)(acc * TN + ch * 32), gv);
                     if (dbg && pass == 0 && nt == 0 && blockIdx.x == 0 && blockIdx.y == 0) {
 #pragma unroll
-                        for (int u = 0; u < 32; ++u) dbg[tid * TN + ch * 32 + u] = gv[u] + 1000.f;
+                        for (int u = 0; u < 32; ++u) dbg[row * TN + ch * 32 + u] = gv[u] + 1000.f;
                     }
                     const float4* nj4 = reinterpret_cast<const float4*>(nrm_s + nt * TN + ch * 32);
 #pragma unroll
@@ -313,11 +323,12 @@ __global__ void __launch_bounds__(TF_T, 1) knn_feat_tc_kernel(const float* __res
                         for (int u = 0; u < 4; ++u) {
                             const float t = __fmaf_rn(-2.f, gv[4 * q + u], njv[u]);
                             if (pass == 0) {
-                                mn[(ch & 3) * 32 + 4 * q + u] = fminf(mn[(ch & 3) * 32 + 4 * q + u], t);   // NaN never wins
+                                // chunk ch covers subgroups (ch % 4) * 32 ..: local slot = lower / upper 32 of this thread's 64
+                                mn[(cq & 1) * 32 + 4 * q + u] = fminf(mn[(cq & 1) * 32 + 4 * q + u], t);   // NaN never wins
                             } else if (t <= ft) {                    // one compare per candidate: ft >= every t with fl(t + ni) <= fv
-                                if (nl < TF_CAP) lst[nl * TF_M + tid] = nt * TN + ch * 32 + 4 * q + u;
-                                else over = true;
-                                nl += nl < TF_CAP ? 1 : 0;
+                                const int slot = atomicAdd(&cnt_s[row], 1);          // the query's two threads share its list
+                                if (slot < TF_CAP) lst[slot * TF_M + row] = nt * TN + ch * 32 + 4 * q + u;
+                                else cnt_s[TF_M + row] = 1;
                             }
                         }
                     }
@@ -326,12 +337,17 @@ __global__ void __launch_bounds__(TF_T, 1) knn_feat_tc_kernel(const float* __res
                 mbar_arrive_plain(&tempty[acc]);                     // this thread has read the accumulator
             }
             if (pass == 0) {
-                // bound: k'-th smallest of the 64 group minima (group = subgroups g and g + 64), bf16 rounded down, clamped at 0
-                auto grp = [&](int i) -> unsigned {
-                    const float h = fmaxf(__fadd_rn(fminf(mn[i], mn[i + 64]), ni), 0.f);
-                    return __float_as_uint(h) >> 16;
-                };
+                // this thread's 32 group minima (group = subgroups s and s + 64), bf16 rounded down, clamped at 0 -> shared memory;
+                // both threads of the query then run the same network over all 64 and get the same threshold
+#pragma unroll
+                for (int i = 0; i < 32; ++i) {
+                    const float h = fmaxf(__fadd_rn(fminf(mn[i], mn[i + 32]), ni), 0.f);
+                    exch[(half * 32 + i) * TF_M + row] = (unsigned short)(__float_as_uint(h) >> 16);
+                }
+                asm volatile("bar.sync 1, 256;" ::: "memory");        // the 8 epilogue warps only
+                auto grp = [&](int i) -> unsigned { return exch[i * TF_M + row]; };
                 const unsigned a16 = kq_kth_of_64(grp, kk);
+                asm volatile("bar.sync 1, 256;" ::: "memory");        // exch is read: the lists may overwrite it
                 if (a16 >= 0x7f80u || !(ni <= 3.402823466e+38f)) {
                     over = true;                                     // fewer than k' finite groups, or a non-finite query
                     fv = -1.f;
@@ -349,15 +365,17 @@ __global__ void __launch_bounds__(TF_T, 1) knn_feat_tc_kernel(const float* __res
                 }
             }
         }
-        // lists out (flag = -1: the exact kernel recomputes this query)
-        const size_t q = (size_t)bz * n + m0 + tid;
-        if (dbg) {
-            cnt[q] = -1;                                             // bring-up dump: the Gram tile sits in the list buffer
-        } else if (over || nl < kk) {
-            cnt[q] = -1;
-        } else {
-            cnt[q] = nl;
-            for (int e = 0; e < nl; ++e) cand[q * TF_CAP + e] = lst[e * TF_M + tid];
+        asm volatile("bar.sync 1, 256;" ::: "memory");                // both halves have appended
+        // lists out (flag = -1: the exact brute force recomputes this query)
+        if (half == 0) {
+            const size_t q = (size_t)bz * n + m0 + row;
+            const int nlist = cnt_s[row];
+            if (dbg || over || cnt_s[TF_M + row] || nlist > TF_CAP || nlist < kk) {
+                cnt[q] = -1;
+            } else {
+                cnt[q] = nlist;
+                for (int e = 0; e < nlist; ++e) cand[q * TF_CAP + e] = lst[e * TF_M + row];
+            }
         }
     }
     kf_fence_before();
@@ -527,7 +545,7 @@ int knn_feat_tc_launch(const float* x, int b, int c, int n, int k, int skip, lon
     const int tn = (n % 256 == 0 && n >= 1024) ? 256 : 128;   // small clouds: more, smaller tiles keep the ring deep
     static const char* tn_env = tune_env("PDGN_KNN_FEAT_TN");
     const int tnsel = (tn_env && atoi(tn_env) == 128) ? 128 : tn;
-    const size_t fixed = (size_t)((c + 31) / 32) * 16384 + (size_t)n * 4 + (size_t)TF_CAP * TF_M * 4, sb = (size_t)(tnsel / 128) * 16384;
+    const size_t fixed = (size_t)((c + 31) / 32) * 16384 + (size_t)n * 4 + (size_t)TF_CAP * TF_M * 4 + 2 * TF_M * 4, sb = (size_t)(tnsel / 128) * 16384;
     int nst = (int)((216 * 1024 - fixed) / sb);
     if (nst > TF_NST) nst = TF_NST;
     if (nst < 2) return PDGN_ERR_UNSUPPORTED;
