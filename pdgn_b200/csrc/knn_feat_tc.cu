@@ -405,17 +405,37 @@ __global__ void __launch_bounds__(256) knn_feat_rerank_kernel(const float* __res
     float* my = rows_s + (size_t)warp * 33 * RR_RS;
     const int half = lane >> 4, li = lane & 15;
     float acc = 0.f;
+    // row 0 = the query, row 1 + l = lane l's candidate; two rows per step, 16 lanes x 16 bytes each.  The first RR_PF steps
+    // (rows 0..15: the whole list in the common case) are software-pipelined through registers: the next round's loads are in
+    // flight while this round's chains run.
+    constexpr int RR_PF = 8;
+    const float* srcp[RR_PF];
+#pragma unroll
+    for (int i = 0; i < RR_PF; ++i) {
+        const int row = 2 * i + half;
+        const int jj = __shfl_sync(kFull, j, max(row - 1, 0));
+        srcp[i] = row > m ? nullptr : (row == 0 ? xT + (size_t)q * c : xT + ((size_t)bz * n + jj) * c);
+    }
+    float4 pf[RR_PF];
+    auto prefetch = [&](int c0) {
+        const int cw = min(RR_CH, c - c0);
+#pragma unroll
+        for (int i = 0; i < RR_PF; ++i)
+            if (srcp[i] && li * 4 < cw) pf[i] = __ldg(reinterpret_cast<const float4*>(srcp[i] + c0) + li);
+    };
+    prefetch(0);
     for (int c0 = 0; c0 < c; c0 += RR_CH) {
         const int cw = min(RR_CH, c - c0);                           // multiple of 4 (c % 8 == 0 on this path)
-        // row 0 = the query, row 1 + l = lane l's candidate; two rows per step, 16 lanes x 16 bytes each
-        for (int r0 = 0; r0 <= m; r0 += 2) {
+#pragma unroll
+        for (int i = 0; i < RR_PF; ++i)
+            if (srcp[i] && li * 4 < cw) *reinterpret_cast<float4*>(my + (2 * i + half) * RR_RS + li * 4) = pf[i];
+        for (int r0 = 2 * RR_PF; r0 <= m; r0 += 2) {                 // lists beyond 15 candidates: straight to shared memory
             const int row = r0 + half;
             const int jj = __shfl_sync(kFull, j, max(row - 1, 0));
-            if (row <= m && li * 4 < cw) {
-                const float* src = row == 0 ? xT + (size_t)q * c : xT + ((size_t)bz * n + jj) * c;
-                *reinterpret_cast<float4*>(my + row * RR_RS + li * 4) = __ldg(reinterpret_cast<const float4*>(src + c0) + li);
-            }
+            if (row <= m && li * 4 < cw)
+                *reinterpret_cast<float4*>(my + row * RR_RS + li * 4) = __ldg(reinterpret_cast<const float4*>(xT + ((size_t)bz * n + jj) * c + c0) + li);
         }
+        if (c0 + RR_CH < c) prefetch(c0 + RR_CH);
         __syncwarp();
         if (j >= 0) {
             const float4* a4 = reinterpret_cast<const float4*>(my);
