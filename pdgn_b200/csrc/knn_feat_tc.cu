@@ -58,10 +58,11 @@ __device__ __forceinline__ float tf32_rn(float v) {
     return __uint_as_float(r);
 }
 
-// one CTA = 32 points of one batch element, all channels
-__global__ void __launch_bounds__(256) kf_prep_kernel(const float* __restrict__ x, const float* __restrict__ mean, int c, int n,
-                                                     float* __restrict__ xc, float* __restrict__ xT, float* __restrict__ nrm,
-                                                     unsigned* __restrict__ maxn) {
+constexpr int KF_SLABS = 4;   // channel slabs of the prep kernel (partial norms per slab, summed in a fixed order by the filter)
+
+// one CTA = 32 points of one batch element x one slab of channels (blockIdx.z; slab = cps channels, a multiple of 32)
+__global__ void __launch_bounds__(256) kf_prep_kernel(const float* __restrict__ x, const float* __restrict__ mean, int c, int n, int cps,
+                                                     float* __restrict__ xc, float* __restrict__ xT, float* __restrict__ nrm) {
     __shared__ float tile[32][33], tilec[32][33];
     __shared__ float part[8][32];
     const int bz = blockIdx.y, n0 = blockIdx.x * 32, tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
@@ -76,7 +77,8 @@ __global__ void __launch_bounds__(256) kf_prep_kernel(const float* __restrict__ 
     float* xtb = xT + (size_t)bz * n * c;
     const float* mb = mean + (size_t)bz * c;
     float acc = 0.f;
-    for (int c0 = 0; c0 < c; c0 += 32) {
+    const int c_lo = blockIdx.z * cps, c_hi = min(c, c_lo + cps);
+    for (int c0 = c_lo; c0 < c_hi; c0 += 32) {
         for (int ch = ty; ch < 32; ch += 8) {
             float v = 0.f, w = 0.f;
             if (c0 + ch < c && n0 + tx < n) {
@@ -102,8 +104,7 @@ __global__ void __launch_bounds__(256) kf_prep_kernel(const float* __restrict__ 
         float s = 0.f;
 #pragma unroll
         for (int r = 0; r < 8; ++r) s += part[r][tx];
-        nrm[(size_t)bz * n + n0 + tx] = s;
-        if (s <= 3.402823466e+38f) atomicMax(&maxn[bz], __float_as_uint(s));   // s >= 0: unsigned order == float order
+        nrm[((size_t)bz * KF_SLABS + blockIdx.z) * n + n0 + tx] = s;          // partial squared norm of this slab (0 for an empty slab)
     }
 }
 
@@ -178,11 +179,12 @@ constexpr int TF_T = TF_E + 32;    // + 1 warp whose lane 0 copies and issues th
 
 template <int TN>
 __global__ void __launch_bounds__(TF_T, 1) knn_feat_tc_kernel(const float* __restrict__ xc, const float* __restrict__ nrm,
-                                                            const unsigned* __restrict__ maxn, int c, int n, int kk,
+                                                            int c, int n, int kk,
                                                             int* __restrict__ cand, int* __restrict__ cnt, int nst, float* __restrict__ dbg, uint32_t idesc) {
     extern __shared__ __align__(1024) unsigned char kf_smem[];
     __shared__ uint64_t bars[TF_NST], fullb[TF_NST], abar, tfull[2], tempty[2];   // bars: stage consumed by the tensor core; fullb: stage filled
     __shared__ uint32_t tmem_slot;
+    __shared__ float wmax[TF_T / 32];
     const int tid = threadIdx.x, warp = tid >> 5;
     const int bz = blockIdx.y, m0 = blockIdx.x * TF_M;
     const int nkb = (c + TF_KB - 1) / TF_KB;                          // K-blocks (channels zero-padded to a multiple of 32)
@@ -217,7 +219,18 @@ __global__ void __launch_bounds__(TF_T, 1) knn_feat_tc_kernel(const float* __res
         for (int kb = 0; kb < nkb; ++kb)
             bulk_g2s(a_sm + (size_t)kb * 16384, xcb + ((size_t)blockIdx.x * nkb + kb) * 4096, 16384u, &abar);
     }
-    for (int j = tid; j < n; j += TF_T) nrm_s[j] = nrm[(size_t)bz * n + j];
+    // squared norms: the prep kernel's per-slab partial sums added in a fixed order; their maximum over the cloud on the way
+    float lmax = 0.f;
+    for (int j = tid; j < n; j += TF_T) {
+        float v = 0.f;
+#pragma unroll
+        for (int sl = 0; sl < KF_SLABS; ++sl) v += nrm[((size_t)bz * KF_SLABS + sl) * n + j];
+        nrm_s[j] = v;
+        if (v <= 3.402823466e+38f) lmax = fmaxf(lmax, v);
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) lmax = fmaxf(lmax, __shfl_xor_sync(kFull, lmax, o));
+    if ((tid & 31) == 0) wmax[warp] = lmax;
     kf_fence_before();
     __syncthreads();
     kf_fence_after();
@@ -227,7 +240,9 @@ __global__ void __launch_bounds__(TF_T, 1) knn_feat_tc_kernel(const float* __res
     const float ni = nrm_s[m0 + (tid & (TF_M - 1))];
     unsigned short* exch = reinterpret_cast<unsigned short*>(lst);   // [2][32][128] group minima between the passes (the lists are idle)
     int* cnt_s = lst + TF_CAP * TF_M;                                // [128] list lengths, [128] overflow flags
-    const float mx = __uint_as_float(maxn[bz]);
+    float mx = 0.f;
+#pragma unroll
+    for (int w = 0; w < TF_T / 32; ++w) mx = fmaxf(mx, wmax[w]);
     const int ntile = n / TN;
     // Epilogue thread (row, half): half h takes the 32-column chunks ch with ch % 2 == h, i.e. the subgroups [32h, 32h + 32) and
     // [64 + 32h, 96 + 32h) -- the two threads of a query own DISJOINT groups (i, i + 64), 32 each.
@@ -534,7 +549,7 @@ bool knn_feat_tc_eligible(int c, int n, int k, int skip) {
 size_t knn_feat_tc_workspace(int b, int c, int n) {
     const size_t bc = (size_t)b * c, bn = (size_t)b * n;
     const size_t cp = (size_t)((c + 31) / 32) * 32;                 // channels padded to whole K-blocks in the tiled copy
-    return kf_align(bc * 4) + kf_align((size_t)b * cp * n * 4) + kf_align(bc * n * 4) + kf_align(bn * 4) + kf_align((size_t)b * 4) + kf_align(bn * TF_CAP * 4) + kf_align(bn * 4) + 256;
+    return kf_align(bc * 4) + kf_align((size_t)b * cp * n * 4) + kf_align(bc * n * 4) + kf_align(bn * KF_SLABS * 4) + kf_align(bn * TF_CAP * 4) + kf_align(bn * 4) + 256;
 }
 
 // Runs prep + filter + re-rank; *flags receives the per-query count array (negative = recompute with the exact kernel).
@@ -548,17 +563,15 @@ int knn_feat_tc_launch(const float* x, int b, int c, int n, int k, int skip, lon
     p += kf_align((size_t)b * ((c + 31) / 32) * 32 * n * 4);
     float* xT = reinterpret_cast<float*>(p);
     p += kf_align(bc * n * 4);
-    float* nrm = reinterpret_cast<float*>(p);
-    p += kf_align(bn * 4);
-    unsigned* maxn = reinterpret_cast<unsigned*>(p);
-    p += kf_align((size_t)b * 4);
+    float* nrm = reinterpret_cast<float*>(p);                       // [b][KF_SLABS][n] partial squared norms
+    p += kf_align(bn * KF_SLABS * 4);
     int* cand = reinterpret_cast<int*>(p);
     p += kf_align(bn * TF_CAP * 4);
     int* cnt = reinterpret_cast<int*>(p);
-    PDGN_CUDA(cudaMemsetAsync(maxn, 0, (size_t)b * 4, st));
     kf_mean_kernel<<<(unsigned)((bc + 7) / 8), 256, 0, st>>>(x, (int)bc, n, mean);
     PDGN_CHECK_LAUNCH();
-    kf_prep_kernel<<<dim3((n + 31) / 32, b), 256, 0, st>>>(x, mean, c, n, xc, xT, nrm, maxn);
+    const int cps = (((c + 31) / 32 + KF_SLABS - 1) / KF_SLABS) * 32;   // channels per slab
+    kf_prep_kernel<<<dim3((n + 31) / 32, b, KF_SLABS), 256, 0, st>>>(x, mean, c, n, cps, xc, xT, nrm);
     PDGN_CHECK_LAUNCH();
     // accumulator tiles of 256 candidates when the cloud allows (half the tcgen05.mma count: the K = 8 instructions are issue /
     // operand-fetch bound, ~0.26 us each at N = 128), ring as deep as shared memory allows (>= 2 stages)
@@ -576,10 +589,10 @@ int knn_feat_tc_launch(const float* x, int b, int c, int n, int k, int skip, lon
     if (tune_env("PDGN_KNN_FEAT_NOEPI")) idesc |= 2u;
     if (tnsel == 256) {
         PDGN_CUDA(cudaFuncSetAttribute(knn_feat_tc_kernel<256>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        knn_feat_tc_kernel<256><<<dim3(n / TF_M, b), TF_T, smem, st>>>(xc, nrm, maxn, c, n, k + skip, cand, cnt, nst, dbg, idesc);
+        knn_feat_tc_kernel<256><<<dim3(n / TF_M, b), TF_T, smem, st>>>(xc, nrm, c, n, k + skip, cand, cnt, nst, dbg, idesc);
     } else {
         PDGN_CUDA(cudaFuncSetAttribute(knn_feat_tc_kernel<128>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        knn_feat_tc_kernel<128><<<dim3(n / TF_M, b), TF_T, smem, st>>>(xc, nrm, maxn, c, n, k + skip, cand, cnt, nst, dbg, idesc);
+        knn_feat_tc_kernel<128><<<dim3(n / TF_M, b), TF_T, smem, st>>>(xc, nrm, c, n, k + skip, cand, cnt, nst, dbg, idesc);
     }
     PDGN_CHECK_LAUNCH();
     const size_t rr_smem = (size_t)8 * 33 * RR_RS * 4;
