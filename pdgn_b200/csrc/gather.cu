@@ -130,10 +130,13 @@ constexpr int CSR_T = 1024;
 
 __host__ __device__ inline int csr_warps(int n) {   // counter rows that fit ~200 KB (power of two, <= 32)
     int w = 32;
-    while (w > 1 && (size_t)w * (size_t)((n + 1) & ~1) * 2 > 160 * 1024) w >>= 1;
+    while (w > 1 && (size_t)w * (size_t)((n + 1) & ~1) * 3 > 160 * 1024) w >>= 1;   // 16-bit counter + 8-bit owner per (warp, target)
     return w;
 }
-static size_t csr_smem_bytes(int n) { return (size_t)csr_warps(n) * (size_t)((n + 1) & ~1) * 2 + (size_t)n * 4 + 32 * 4; }
+static size_t csr_smem_bytes(int n) { return (size_t)csr_warps(n) * (size_t)((n + 1) & ~1) * 3 + (size_t)n * 4 + 32 * 4 + 16; }
+// staging area for the lists (mk ints) when it fits beside the counters
+static bool csr_stage(int n, long long mk) { return csr_smem_bytes(n) + (size_t)mk * 4 <= 200 * 1024; }
+static size_t csr_smem_total(int n, long long mk) { return csr_smem_bytes(n) + (csr_stage(n, mk) ? (size_t)mk * 4 : 0); }
 // shapes the kernel takes: counters of a (warp, target) pair are 16 bit, the counter block must fit shared memory
 static bool csr_ok(int n, long long mk) {
     const int w = csr_warps(n);
@@ -143,12 +146,16 @@ static bool csr_ok(int n, long long mk) {
 
 template <typename IdxT>
 __global__ void __launch_bounds__(CSR_T) csr_build_kernel(const IdxT* __restrict__ idx, int n, int mk, int* __restrict__ offs,
-                                                         int* __restrict__ pos) {
+                                                         int* __restrict__ pos, int stage_pos) {
     extern __shared__ __align__(16) unsigned char csr_raw[];
     const int W = csr_warps(n), np = (n + 1) & ~1;
     unsigned short* cnt = reinterpret_cast<unsigned short*>(csr_raw);                 // [W][np]
     int* base = reinterpret_cast<int*>(csr_raw + (size_t)W * np * 2);               // [n] first slot of each target's list
     int* wsum = base + n;                                                            // [32]
+    unsigned char* owner = reinterpret_cast<unsigned char*>(wsum + 32);              // [W][np] duplicate detection, fill pass
+    // stage_pos: the lists are assembled in shared memory and written out coalesced.  Scattered 4-byte global stores from ONE SM
+    // per batch element (32 sectors per warp store) were the fill pass's bound: 6 of the kernel's 11 us.
+    int* pos_s = reinterpret_cast<int*>(csr_raw + (((size_t)W * np * 3 + (size_t)n * 4 + 32 * 4 + 15) & ~(size_t)15));
     const int bz = blockIdx.x, t = threadIdx.x, lane = t & 31, warp = t >> 5;
     const IdxT* ip = idx + (size_t)bz * mk;
     int* ob = offs + (size_t)bz * (n + 1);
@@ -229,17 +236,37 @@ __global__ void __launch_bounds__(CSR_T) csr_build_kernel(const IdxT* __restrict
     // fill: the warp walks its slice in order, 32 entries at a time
     const unsigned lt = (1u << lane) - 1u;
     unsigned short* cur = cnt + (size_t)(warp < W ? warp : 0) * np;
+    // Rank of a lane among the lanes of its 32-entry group with the same target.  __match_any_sync costs ~1000 cycles when the
+    // 32 targets are (nearly) all different -- the common case, and 70 % of this kernel's time in the first version -- so the
+    // lanes find out whether they share a target by writing their lane number into a per-warp byte array indexed by target
+    // and reading it back: a lane that reads another lane's number shares its target.  Only those targets (usually none or one,
+    // or one hub) are ranked, one ballot each.
+    unsigned char* own = owner + (size_t)(warp < W ? warp : 0) * np;
     auto place = [&](int e, bool valid, int tgt_in) {
-        const int tgt = valid ? tgt_in : -1 - lane;                       // invalid lanes match nobody
-        const unsigned peers = __match_any_sync(kFull, tgt);
+        const int tgt = valid ? tgt_in : 0;
+        if (valid) own[tgt] = (unsigned char)lane;
+        __syncwarp();
+        const bool lost = valid && own[tgt] != (unsigned char)lane;
+        unsigned dm = __ballot_sync(kFull, lost);
+        unsigned peers = valid ? (1u << lane) : 0u;                      // alone unless shown otherwise
+        while (dm) {                                                      // warp-uniform: one round per target that occurs twice or more
+            const int src = __ffs((int)dm) - 1;
+            const int tdup = __shfl_sync(kFull, tgt, src);
+            const unsigned same = __ballot_sync(kFull, valid && tgt == tdup);
+            if (valid && tgt == tdup) peers = same;
+            dm &= ~same;
+        }
         const int rank = __popc(peers & lt);
         int first = 0;
         if (valid && rank == 0) {                                         // one leader per distinct target of the group
             first = cur[tgt];
             cur[tgt] = (unsigned short)(first + __popc(peers));
         }
-        first = __shfl_sync(kFull, first, __ffs(peers) - 1);
-        if (valid) pb[base[tgt] + first + rank] = e;
+        first = __shfl_sync(kFull, first, peers ? __ffs((int)peers) - 1 : lane);
+        if (valid) {
+            if (stage_pos) pos_s[base[tgt] + first + rank] = e;
+            else pb[base[tgt] + first + rank] = e;
+        }
         __syncwarp();
     };
     if (cached) {
@@ -254,6 +281,10 @@ __global__ void __launch_bounds__(CSR_T) csr_build_kernel(const IdxT* __restrict
             const int e = e0 + lane;
             place(e, e < e_hi, e < e_hi ? (int)ip[e] : 0);
         }
+    }
+    if (stage_pos) {
+        __syncthreads();
+        for (int i = t; i < mk; i += CSR_T) pb[i] = pos_s[i];
     }
 }
 
@@ -632,7 +663,7 @@ extern "C" int pdgn_group_bwd_ws(const float* grad_out, const int* idx, int b, i
     PDGN_VERIFY_IDX32(idx, (size_t)b * m * k, n, (cudaStream_t)stream);
     if (mk > 0x7fffffffLL || b > 65535) return PDGN_ERR_UNSUPPORTED;
     const size_t row_bytes = (size_t)mk * 4;
-    const size_t csr_smem = csr_smem_bytes(n);
+    const size_t csr_smem = csr_smem_total(n, mk);
     if (!workspace || c < 4 || row_bytes > 200 * 1024 || !csr_ok(n, mk))
         return pdgn_group_bwd(grad_out, idx, b, c, n, m, k, grad_points, stream);
     if (workspace_bytes < pdgn_group_bwd_workspace(b, n, m, k) - 256 || (reinterpret_cast<uintptr_t>(workspace) & 3)) return PDGN_ERR_WORKSPACE;
@@ -640,7 +671,7 @@ extern "C" int pdgn_group_bwd_ws(const float* grad_out, const int* idx, int b, i
     int* offs = reinterpret_cast<int*>(workspace);
     int* pos = offs + (size_t)b * (n + 1);
     PDGN_CUDA(cudaFuncSetAttribute(csr_build_kernel<int>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)csr_smem));
-    csr_build_kernel<int><<<b, CSR_T, csr_smem, st>>>(idx, n, (int)mk, offs, pos);
+    csr_build_kernel<int><<<b, CSR_T, csr_smem, st>>>(idx, n, (int)mk, offs, pos, csr_stage(n, mk) ? 1 : 0);
     PDGN_CHECK_LAUNCH();
     bool launched = false;
     const int rc_stream = pull_stream_launch(0, grad_out, offs, pos, b, c, n, (int)mk, 0, grad_points, st, &launched, nullptr);
@@ -729,7 +760,7 @@ extern "C" int pdgn_interp_bwd_ws(const float* grad_out, const int* idx, const f
     PDGN_GATHER_ARGS_OK(grad_out && idx && weight && grad_points && m > 0);
     PDGN_VERIFY_IDX32(idx, (size_t)b * n * 3, m, (cudaStream_t)stream);
     if (b > 65535) return PDGN_ERR_UNSUPPORTED;
-    const size_t csr_smem = csr_smem_bytes(m);
+    const size_t csr_smem = csr_smem_total(m, (long long)n * 3);
     int cc = PULL_CC;
     while (cc > 1 && ((size_t)cc * n + 3 * (size_t)n) * 4 > 96 * 1024) cc >>= 1;
     const size_t smem = ((size_t)cc * n + 3 * (size_t)n) * 4;
@@ -740,7 +771,7 @@ extern "C" int pdgn_interp_bwd_ws(const float* grad_out, const int* idx, const f
     int* offs = reinterpret_cast<int*>(workspace);
     int* pos = offs + (size_t)b * (m + 1);
     PDGN_CUDA(cudaFuncSetAttribute(csr_build_kernel<int>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)csr_smem));
-    csr_build_kernel<int><<<b, CSR_T, csr_smem, st>>>(idx, m, 3 * n, offs, pos);
+    csr_build_kernel<int><<<b, CSR_T, csr_smem, st>>>(idx, m, 3 * n, offs, pos, csr_stage(m, (long long)n * 3) ? 1 : 0);
     PDGN_CHECK_LAUNCH();
     {   // streaming form (TMA double-buffered rows, register-cached lists and weights): any shape it accepts
         bool launched = false;
@@ -824,7 +855,7 @@ extern "C" int pdgn_edge_feat_bwd_ws(const float* grad_ee, const int64_t* idx, i
     PDGN_VERIFY_IDX64(idx, (size_t)b * n * k, n, (cudaStream_t)stream);
     if (b > 65535) return PDGN_ERR_UNSUPPORTED;
     const long long nk = (long long)n * k;
-    const size_t csr_smem = csr_smem_bytes(n);
+    const size_t csr_smem = csr_smem_total(n, nk);
     const size_t row_bytes = (size_t)nk * 4;  // the g1 row of one channel
     if (!workspace || row_bytes > 200 * 1024 || !csr_ok(n, nk))
         return pdgn_edge_feat_bwd(grad_ee, idx, b, c, n, k, grad_x, stream);
@@ -833,7 +864,7 @@ extern "C" int pdgn_edge_feat_bwd_ws(const float* grad_ee, const int64_t* idx, i
     int* offs = reinterpret_cast<int*>(workspace);
     int* pos = offs + (size_t)b * (n + 1);
     PDGN_CUDA(cudaFuncSetAttribute(csr_build_kernel<long long>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)csr_smem));
-    csr_build_kernel<long long><<<b, CSR_T, csr_smem, st>>>(reinterpret_cast<const long long*>(idx), n, (int)nk, offs, pos);
+    csr_build_kernel<long long><<<b, CSR_T, csr_smem, st>>>(reinterpret_cast<const long long*>(idx), n, (int)nk, offs, pos, csr_stage(n, nk) ? 1 : 0);
     PDGN_CHECK_LAUNCH();
     bool launched = false;
     const int rc_stream = pull_stream_launch(1, grad_ee, offs, pos, b, c, n, (int)nk, k, grad_x, st, &launched, nullptr);
