@@ -38,7 +38,7 @@ constexpr int TF_M = 128;    // queries per CTA = TMEM lanes
 constexpr int TF_SG = 128;   // strided subgroups of the bound (candidate j -> subgroup j % 128); accumulator tiles are 128 or 256 wide
 constexpr int TF_KB = 32;    // channels per staged K-block (4 MMAs of K = 8)
 constexpr int TF_NST = 4;    // B ring stages (3 when the norms of a large cloud need the room)
-constexpr int TF_CAP = 32;   // list entries per query
+constexpr int TF_CAP = 64;   // list entries per query (global memory; the re-rank takes 32 in its fast pass, the rest one by one)
 constexpr int TF_KMAX = 20;  // k + skip the bound network is tuned for (expected list: -ln(1 - k'/64) * 64 + margin)
 
 // ---------------------------------------------------------------- prep
@@ -239,7 +239,7 @@ __global__ void __launch_bounds__(TF_T, 1) knn_feat_tc_kernel(const float* __res
 
     const float ni = nrm_s[m0 + (tid & (TF_M - 1))];
     unsigned short* exch = reinterpret_cast<unsigned short*>(lst);   // [2][32][128] group minima between the passes (the lists are idle)
-    int* cnt_s = lst + TF_CAP * TF_M;                                // [128] list lengths, [128] overflow flags
+    int* cnt_s = lst + 32 * TF_M;                                    // [128] list lengths, [128] overflow flags (after the 16 KB exchange area)
     float mx = 0.f;
 #pragma unroll
     for (int w = 0; w < TF_T / 32; ++w) mx = fmaxf(mx, wmax[w]);
@@ -342,7 +342,7 @@ __global__ void __launch_bounds__(TF_T, 1) knn_feat_tc_kernel(const float* __res
                                 mn[(cq & 1) * 32 + 4 * q + u] = fminf(mn[(cq & 1) * 32 + 4 * q + u], t);   // NaN never wins
                             } else if (t <= ft) {                    // one compare per candidate: ft >= every t with fl(t + ni) <= fv
                                 const int slot = atomicAdd(&cnt_s[row], 1);          // the query's two threads share its list
-                                if (slot < TF_CAP) lst[slot * TF_M + row] = nt * TN + ch * 32 + 4 * q + u;
+                                if (slot < TF_CAP) cand[((size_t)bz * n + m0 + row) * TF_CAP + slot] = nt * TN + ch * 32 + 4 * q + u;
                                 else cnt_s[TF_M + row] = 1;
                             }
                         }
@@ -388,8 +388,7 @@ __global__ void __launch_bounds__(TF_T, 1) knn_feat_tc_kernel(const float* __res
             if (dbg || over || cnt_s[TF_M + row] || nlist > TF_CAP || nlist < kk) {
                 cnt[q] = -1;
             } else {
-                cnt[q] = nlist;
-                for (int e = 0; e < nlist; ++e) cand[q * TF_CAP + e] = lst[e * TF_M + row];
+                cnt[q] = nlist;                                       // the entries are already in cand[q][0..nlist)
             }
         }
     }
@@ -404,6 +403,9 @@ __global__ void __launch_bounds__(TF_T, 1) knn_feat_tc_kernel(const float* __res
 // lane then walks its own row from there: the first version let every lane read its row straight from global memory (16 bytes
 // per lane and request, 14+ lines per warp request) and ran at 3.5 TB/s of L2 traffic.  The chain stays strictly sequential
 // in c (the accumulator is carried across the 64-channel rounds).
+__device__ __noinline__ void kf_brute_query(const float* __restrict__ xT, int q, int c, int n, int k, int skip, int lane, float* __restrict__ dsm,
+                               long long* __restrict__ idx, float* __restrict__ dist2);
+
 constexpr int RR_CH = 64;            // channels per round
 constexpr int RR_RS = RR_CH + 4;     // row stride in floats: 272 bytes, conflict-free LDS.128 for 32 lanes on 32 different rows
 __global__ void __launch_bounds__(256) knn_feat_rerank_kernel(const float* __restrict__ xT, const int* __restrict__ cand,
@@ -413,11 +415,16 @@ __global__ void __launch_bounds__(256) knn_feat_rerank_kernel(const float* __res
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int q = blockIdx.x * 8 + warp;
     if (q >= total) return;
-    const int m = cnt[q];
-    if (m < 0) return;                                               // flagged: the exact kernel writes this query
-    const int bz = q / n;
-    const int j = lane < m ? cand[(size_t)q * TF_CAP + lane] : -1;
+    const int mraw = cnt[q];
+    const int m = min(mraw, 32);
     float* my = rows_s + (size_t)warp * 33 * RR_RS;
+    if (mraw < 0) {                                                     // flagged by the filter: exact brute force (few queries)
+        if (n <= 33 * RR_RS) kf_brute_query(xT, q, c, n, k, skip, lane, my, idx, dist2);   // else knn_feat_brute_kernel
+        return;
+    }
+    const int bz = q / n;
+    const int mfull = mraw;                                          // up to TF_CAP entries; the staged pass below takes the first 32
+    const int j = lane < mfull ? cand[(size_t)q * TF_CAP + lane] : -1;
     const int half = lane >> 4, li = lane & 15;
     float acc = 0.f;
     // row 0 = the query, row 1 + l = lane l's candidate; two rows per step, 16 lanes x 16 bytes each.  The first RR_PF steps
@@ -470,13 +477,51 @@ __global__ void __launch_bounds__(256) knn_feat_rerank_kernel(const float* __res
         }
         __syncwarp();
     }
+    // entries 32..63 (rare: the list is ~14 long): one more candidate per lane, its row read straight from global memory
+    int j1 = -1;
+    float acc1 = 0.f;
+    if (mfull > 32) {                                                // warp-uniform
+        j1 = lane + 32 < mfull ? cand[(size_t)q * TF_CAP + 32 + lane] : -1;
+        if (j1 >= 0) {
+            const float* xi = xT + (size_t)q * c;
+            const float* xj = xT + ((size_t)bz * n + j1) * c;
+            for (int ch = 0; ch < c; ch += 4) {
+                const float4 a = __ldg(reinterpret_cast<const float4*>(xi + ch)), b = __ldg(reinterpret_cast<const float4*>(xj + ch));
+                float d = __fsub_rn(a.x, b.x);
+                acc1 = __fmaf_rn(d, d, acc1);
+                d = __fsub_rn(a.y, b.y);
+                acc1 = __fmaf_rn(d, d, acc1);
+                d = __fsub_rn(a.z, b.z);
+                acc1 = __fmaf_rn(d, d, acc1);
+                d = __fsub_rn(a.w, b.w);
+                acc1 = __fmaf_rn(d, d, acc1);
+            }
+        }
+    }
     const unsigned long long key = j >= 0 ? (((unsigned long long)__float_as_uint(acc) << 32) | (unsigned)j) : ~0ull;
-    int rank = 0;
+    const unsigned long long key1 = j1 >= 0 ? (((unsigned long long)__float_as_uint(acc1) << 32) | (unsigned)j1) : ~0ull;
+    int rank = 0, rank1 = 0;
 #pragma unroll
-    for (int o = 0; o < 32; ++o) rank += __shfl_sync(kFull, key, o) < key ? 1 : 0;
+    for (int o = 0; o < 32; ++o) {
+        const unsigned long long a = __shfl_sync(kFull, key, o);
+        rank += a < key ? 1 : 0;
+        rank1 += a < key1 ? 1 : 0;
+    }
+    if (mfull > 32) {
+#pragma unroll
+        for (int o = 0; o < 32; ++o) {
+            const unsigned long long b = __shfl_sync(kFull, key1, o);
+            rank += b < key ? 1 : 0;
+            rank1 += b < key1 ? 1 : 0;
+        }
+    }
     if (j >= 0 && rank >= skip && rank < skip + k) {
         idx[(size_t)q * k + rank - skip] = j;
         if (dist2) dist2[(size_t)q * k + rank - skip] = acc;
+    }
+    if (j1 >= 0 && rank1 >= skip && rank1 < skip + k) {
+        idx[(size_t)q * k + rank1 - skip] = j1;
+        if (dist2) dist2[(size_t)q * k + rank1 - skip] = acc1;
     }
 }
 
@@ -485,15 +530,9 @@ __global__ void __launch_bounds__(256) knn_feat_rerank_kernel(const float* __res
 // reference distances of its query once into shared memory and selects ranks skip..skip+k-1 by repeated minimum search over the
 // (d2, index) keys.  Non-finite distances are never selected and missing ranks read index 0 / +inf, exactly like
 // knn_feat_kernel's insertion list (knn_feat.cu), whose per-CTA cost (64 queries at a time) made one flagged query a 0.3 ms tail.
-__global__ void __launch_bounds__(256) knn_feat_brute_kernel(const float* __restrict__ xT, const int* __restrict__ cnt, int c, int n,
-                                                            int k, int skip, int total, long long* __restrict__ idx,
-                                                            float* __restrict__ dist2) {
-    extern __shared__ __align__(16) float bd_s[];                    // [8 warps][n]
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int q = blockIdx.x * 8 + warp;
-    if (q >= total || cnt[q] >= 0) return;
+__device__ __noinline__ void kf_brute_query(const float* __restrict__ xT, int q, int c, int n, int k, int skip, int lane, float* __restrict__ dsm,
+                               long long* __restrict__ idx, float* __restrict__ dist2) {
     const int bz = q / n;
-    float* dsm = bd_s + (size_t)warp * n;
     const float* xi = xT + (size_t)q * c;
     for (int t = lane; t < n; t += 32) {
         const float* xj = xT + ((size_t)bz * n + t) * c;
@@ -540,6 +579,17 @@ __global__ void __launch_bounds__(256) knn_feat_brute_kernel(const float* __rest
     }
 }
 
+// clouds too large for the re-rank kernel's row tile to hold their n distances: a separate launch with n floats per warp
+__global__ void __launch_bounds__(256) knn_feat_brute_kernel(const float* __restrict__ xT, const int* __restrict__ cnt, int c, int n,
+                                                            int k, int skip, int total, long long* __restrict__ idx,
+                                                            float* __restrict__ dist2) {
+    extern __shared__ __align__(16) float bd_s[];                    // [8 warps][n]
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int q = blockIdx.x * 8 + warp;
+    if (q >= total || cnt[q] >= 0) return;
+    kf_brute_query(xT, q, c, n, k, skip, lane, bd_s + (size_t)warp * n, idx, dist2);
+}
+
 // ---------------------------------------------------------------- host side
 static size_t kf_align(size_t v) { return (v + 255) & ~(size_t)255; }
 
@@ -578,7 +628,7 @@ int knn_feat_tc_launch(const float* x, int b, int c, int n, int k, int skip, lon
     const int tn = (n % 256 == 0 && n >= 1024) ? 256 : 128;   // small clouds: more, smaller tiles keep the ring deep
     static const char* tn_env = tune_env("PDGN_KNN_FEAT_TN");
     const int tnsel = (tn_env && atoi(tn_env) == 128) ? 128 : tn;
-    const size_t fixed = (size_t)((c + 31) / 32) * 16384 + (size_t)n * 4 + (size_t)TF_CAP * TF_M * 4 + 2 * TF_M * 4, sb = (size_t)(tnsel / 128) * 16384;
+    const size_t fixed = (size_t)((c + 31) / 32) * 16384 + (size_t)n * 4 + (size_t)32 * TF_M * 4 + 2 * TF_M * 4, sb = (size_t)(tnsel / 128) * 16384;
     int nst = (int)((216 * 1024 - fixed) / sb);
     if (nst > TF_NST) nst = TF_NST;
     if (nst < 2) return PDGN_ERR_UNSUPPORTED;
@@ -599,10 +649,12 @@ int knn_feat_tc_launch(const float* x, int b, int c, int n, int k, int skip, lon
     PDGN_CUDA(cudaFuncSetAttribute(knn_feat_rerank_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)rr_smem));
     knn_feat_rerank_kernel<<<(unsigned)((bn + 7) / 8), 256, rr_smem, st>>>(xT, cand, cnt, c, n, k, skip, (int)bn, idx, dist2);
     PDGN_CHECK_LAUNCH();
-    const size_t bf_smem = (size_t)8 * n * 4;
-    PDGN_CUDA(cudaFuncSetAttribute(knn_feat_brute_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bf_smem));
-    knn_feat_brute_kernel<<<(unsigned)((bn + 7) / 8), 256, bf_smem, st>>>(xT, cnt, c, n, k, skip, (int)bn, idx, dist2);
-    PDGN_CHECK_LAUNCH();
+    if (n > 33 * RR_RS) {                                            // larger clouds: the flagged queries in their own launch
+        const size_t bf_smem = (size_t)8 * n * 4;
+        PDGN_CUDA(cudaFuncSetAttribute(knn_feat_brute_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bf_smem));
+        knn_feat_brute_kernel<<<(unsigned)((bn + 7) / 8), 256, bf_smem, st>>>(xT, cnt, c, n, k, skip, (int)bn, idx, dist2);
+        PDGN_CHECK_LAUNCH();
+    }
     *flags = nullptr;                                                // nothing left for the caller to recompute
     return PDGN_OK;
 }

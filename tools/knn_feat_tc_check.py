@@ -22,7 +22,7 @@ def run(x, k, skip, simt=False):
     check(L.pdgn_knn_feat_ws(x.data_ptr(), b, c, n, k, skip, idx.data_ptr(), d2.data_ptr(), ws.data_ptr(), wsb, st), "ws")
     torch.cuda.synchronize()
     base = (ws.data_ptr() + 255) & ~255
-    off = base - ws.data_ptr() + al(b * c * 4) + al(b * ((c + 31) // 32) * 32 * n * 4) + al(b * c * n * 4) + al(b * n * 4 * 4) + al(b * n * 32 * 4)
+    off = base - ws.data_ptr() + al(b * c * 4) + al(b * ((c + 31) // 32) * 32 * n * 4) + al(b * c * n * 4) + al(b * n * 4 * 4) + al(b * n * 64 * 4)
     cnt = ws[off: off + b * n * 4].view(torch.int32).cpu().numpy()
     return idx, d2, cnt
 
