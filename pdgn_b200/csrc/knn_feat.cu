@@ -23,7 +23,8 @@ constexpr int FCK = 32;   // channels staged per step
 // a CTA without one returns at once.
 __global__ void __launch_bounds__(FT) knn_feat_kernel(const float* __restrict__ x, int c, int n, int k, int skip,
                                                      long long* __restrict__ idx, float* __restrict__ dist2,
-                                                     const int* __restrict__ flags) {
+                                                     const int* __restrict__ flags, const int* __restrict__ nflag, int brute_max,
+                                                     int brute_n_max) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     float* xi = reinterpret_cast<float*>(smem_raw);  // [FCK][FB]
     float* xj = xi + FCK * FB;                       // [FCK][FB]
@@ -38,6 +39,8 @@ __global__ void __launch_bounds__(FT) knn_feat_kernel(const float* __restrict__ 
     const float* xb = x + (size_t)bz * c * n;
     bool mine = true;
     if (flags) {
+        // the tensor-core path's re-rank kernel has already recomputed the flagged queries when they were few (and the cloud small)
+        if (*nflag == 0 || (*nflag <= brute_max && n <= brute_n_max)) return;
         mine = t < FB && i0 + t < n && flags[(size_t)bz * n + i0 + t] < 0;
         if (!__syncthreads_or(mine ? 1 : 0)) return;
     }
@@ -118,16 +121,17 @@ extern "C" int pdgn_knn_feat(const float* x, int b, int c, int n, int k, int ski
     const size_t smem = (size_t)(2 * FCK * FB + FB * (FB + 1)) * 4 + (size_t)(k + skip) * FB * 8;
     PDGN_CUDA(cudaFuncSetAttribute(knn_feat_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     dim3 grid((n + FB - 1) / FB, b);
-    knn_feat_kernel<<<grid, FT, smem, (cudaStream_t)stream>>>(x, c, n, k, skip, reinterpret_cast<long long*>(idx), dist2, nullptr);
+    knn_feat_kernel<<<grid, FT, smem, (cudaStream_t)stream>>>(x, c, n, k, skip, reinterpret_cast<long long*>(idx), dist2, nullptr, nullptr, 0, 0);
     PDGN_CHECK_LAUNCH();
     return PDGN_OK;
 }
 
 namespace pdgn {
 bool knn_feat_tc_eligible(int c, int n, int k, int skip);
+int knn_feat_tc_brute_max();
 size_t knn_feat_tc_workspace(int b, int c, int n);
 int knn_feat_tc_launch(const float* x, int b, int c, int n, int k, int skip, long long* idx, float* dist2, void* ws, const int** flags,
-                       cudaStream_t st);
+                       const int** nflag_out, int* brute_n_max, cudaStream_t st);
 }  // namespace pdgn
 
 // Workspace form: the tensor-core filter + exact re-rank of knn_feat_tc.cu for the shapes it takes (8 <= c <= 256, c % 8 == 0,
@@ -145,13 +149,15 @@ extern "C" int pdgn_knn_feat_ws(const float* x, int b, int c, int n, int k, int 
     if (!workspace || !knn_feat_tc_eligible(c, n, k, skip) || b > 65535 || b == 0 || (impl && impl[0] == 's'))
         return pdgn_knn_feat(x, b, c, n, k, skip, idx, dist2, stream);
     if (workspace_bytes < knn_feat_tc_workspace(b, c, n) - 256) return PDGN_ERR_WORKSPACE;
-    const int* flags = nullptr;
-    const int rc = knn_feat_tc_launch(x, b, c, n, k, skip, reinterpret_cast<long long*>(idx), dist2, workspace, &flags, (cudaStream_t)stream);
+    const int *flags = nullptr, *nflag = nullptr;
+    int brute_n_max = 0;
+    const int rc = knn_feat_tc_launch(x, b, c, n, k, skip, reinterpret_cast<long long*>(idx), dist2, workspace, &flags, &nflag, &brute_n_max,
+                                      (cudaStream_t)stream);
     if (rc != PDGN_OK || !flags) return rc;
     const size_t smem = (size_t)(2 * FCK * FB + FB * (FB + 1)) * 4 + (size_t)(k + skip) * FB * 8;
     PDGN_CUDA(cudaFuncSetAttribute(knn_feat_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     dim3 grid((n + FB - 1) / FB, b);
-    knn_feat_kernel<<<grid, FT, smem, (cudaStream_t)stream>>>(x, c, n, k, skip, reinterpret_cast<long long*>(idx), dist2, flags);
+    knn_feat_kernel<<<grid, FT, smem, (cudaStream_t)stream>>>(x, c, n, k, skip, reinterpret_cast<long long*>(idx), dist2, flags, nflag, knn_feat_tc_brute_max(), brute_n_max);
     PDGN_CHECK_LAUNCH();
     return PDGN_OK;
 }

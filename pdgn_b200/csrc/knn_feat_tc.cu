@@ -42,7 +42,9 @@ constexpr int TF_CAP = 64;   // list entries per query (global memory; the re-ra
 constexpr int TF_KMAX = 20;  // k + skip the bound network is tuned for (expected list: -ln(1 - k'/64) * 64 + margin)
 
 // ---------------------------------------------------------------- prep
-__global__ void __launch_bounds__(256) kf_mean_kernel(const float* __restrict__ x, int rows, int n, float* __restrict__ mean) {
+__global__ void __launch_bounds__(256) kf_mean_kernel(const float* __restrict__ x, int rows, int n, float* __restrict__ mean,
+                                                     int* __restrict__ nflag) {
+    if (blockIdx.x == 0 && threadIdx.x == 0) *nflag = 0;            // the filter (two launches later) counts its flagged queries here
     const int row = blockIdx.x * 8 + (threadIdx.x >> 5), lane = threadIdx.x & 31;
     if (row >= rows) return;
     const float* p = x + (size_t)row * n;
@@ -58,6 +60,8 @@ __device__ __forceinline__ float tf32_rn(float v) {
     return __uint_as_float(r);
 }
 
+constexpr int KF_BRUTE_MAX = 512;   // flagged queries the re-rank kernel recomputes itself (one warp each, ~0.3 ms of latency); beyond
+                                    // that (degenerate clouds: every query flagged) knn_feat.cu's 64-query CTAs are the faster fallback
 constexpr int KF_SLABS = 4;   // channel slabs of the prep kernel (partial norms per slab, summed in a fixed order by the filter)
 
 // one CTA = 32 points of one batch element x one slab of channels (blockIdx.z; slab = cps channels, a multiple of 32)
@@ -180,7 +184,8 @@ constexpr int TF_T = TF_E + 32;    // + 1 warp whose lane 0 copies and issues th
 template <int TN>
 __global__ void __launch_bounds__(TF_T, 1) knn_feat_tc_kernel(const float* __restrict__ xc, const float* __restrict__ nrm,
                                                             int c, int n, int kk,
-                                                            int* __restrict__ cand, int* __restrict__ cnt, int nst, float* __restrict__ dbg, uint32_t idesc) {
+                                                            int* __restrict__ cand, int* __restrict__ cnt, int* __restrict__ nflag, int nst, float* __restrict__ dbg,
+                                                            uint32_t idesc) {
     extern __shared__ __align__(1024) unsigned char kf_smem[];
     __shared__ uint64_t bars[TF_NST], fullb[TF_NST], abar, tfull[2], tempty[2];   // bars: stage consumed by the tensor core; fullb: stage filled
     __shared__ uint32_t tmem_slot;
@@ -387,6 +392,7 @@ __global__ void __launch_bounds__(TF_T, 1) knn_feat_tc_kernel(const float* __res
             const int nlist = cnt_s[row];
             if (dbg || over || cnt_s[TF_M + row] || nlist > TF_CAP || nlist < kk) {
                 cnt[q] = -1;
+                atomicAdd(nflag, 1);                                  // how many: decides who recomputes them (KF_BRUTE_MAX)
             } else {
                 cnt[q] = nlist;                                       // the entries are already in cand[q][0..nlist)
             }
@@ -409,8 +415,8 @@ __device__ __noinline__ void kf_brute_query(const float* __restrict__ xT, int q,
 constexpr int RR_CH = 64;            // channels per round
 constexpr int RR_RS = RR_CH + 4;     // row stride in floats: 272 bytes, conflict-free LDS.128 for 32 lanes on 32 different rows
 __global__ void __launch_bounds__(256) knn_feat_rerank_kernel(const float* __restrict__ xT, const int* __restrict__ cand,
-                                                             const int* __restrict__ cnt, int c, int n, int k, int skip, int total,
-                                                             long long* __restrict__ idx, float* __restrict__ dist2) {
+                                                             const int* __restrict__ cnt, const int* __restrict__ nflag, int c, int n, int k,
+                                                             int skip, int total, long long* __restrict__ idx, float* __restrict__ dist2) {
     extern __shared__ __align__(16) float rows_s[];                  // [8 warps][33 rows][RR_RS]
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int q = blockIdx.x * 8 + warp;
@@ -419,8 +425,8 @@ __global__ void __launch_bounds__(256) knn_feat_rerank_kernel(const float* __res
     const int m = min(mraw, 32);
     float* my = rows_s + (size_t)warp * 33 * RR_RS;
     if (mraw < 0) {                                                     // flagged by the filter: exact brute force (few queries)
-        if (n <= 33 * RR_RS) kf_brute_query(xT, q, c, n, k, skip, lane, my, idx, dist2);   // else knn_feat_brute_kernel
-        return;
+        if (n <= 33 * RR_RS && *nflag <= KF_BRUTE_MAX) kf_brute_query(xT, q, c, n, k, skip, lane, my, idx, dist2);
+        return;                                                      // otherwise knn_feat.cu's kernel recomputes it
     }
     const int bz = q / n;
     const int mfull = mraw;                                          // up to TF_CAP entries; the staged pass below takes the first 32
@@ -579,19 +585,10 @@ __device__ __noinline__ void kf_brute_query(const float* __restrict__ xT, int q,
     }
 }
 
-// clouds too large for the re-rank kernel's row tile to hold their n distances: a separate launch with n floats per warp
-__global__ void __launch_bounds__(256) knn_feat_brute_kernel(const float* __restrict__ xT, const int* __restrict__ cnt, int c, int n,
-                                                            int k, int skip, int total, long long* __restrict__ idx,
-                                                            float* __restrict__ dist2) {
-    extern __shared__ __align__(16) float bd_s[];                    // [8 warps][n]
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int q = blockIdx.x * 8 + warp;
-    if (q >= total || cnt[q] >= 0) return;
-    kf_brute_query(xT, q, c, n, k, skip, lane, bd_s + (size_t)warp * n, idx, dist2);
-}
-
 // ---------------------------------------------------------------- host side
 static size_t kf_align(size_t v) { return (v + 255) & ~(size_t)255; }
+
+int knn_feat_tc_brute_max() { return KF_BRUTE_MAX; }
 
 bool knn_feat_tc_eligible(int c, int n, int k, int skip) {
     return c >= 8 && c <= 256 && (c & 7) == 0 && n >= 128 && n <= 4096 && (n & 127) == 0 && k + skip <= TF_KMAX && k >= 1;
@@ -599,12 +596,12 @@ bool knn_feat_tc_eligible(int c, int n, int k, int skip) {
 size_t knn_feat_tc_workspace(int b, int c, int n) {
     const size_t bc = (size_t)b * c, bn = (size_t)b * n;
     const size_t cp = (size_t)((c + 31) / 32) * 32;                 // channels padded to whole K-blocks in the tiled copy
-    return kf_align(bc * 4) + kf_align((size_t)b * cp * n * 4) + kf_align(bc * n * 4) + kf_align(bn * KF_SLABS * 4) + kf_align(bn * TF_CAP * 4) + kf_align(bn * 4) + 256;
+    return kf_align(bc * 4) + kf_align((size_t)b * cp * n * 4) + kf_align(bc * n * 4) + kf_align(bn * KF_SLABS * 4) + kf_align(bn * TF_CAP * 4) + kf_align(bn * 4) + 256 + 256;
 }
 
 // Runs prep + filter + re-rank; *flags receives the per-query count array (negative = recompute with the exact kernel).
 int knn_feat_tc_launch(const float* x, int b, int c, int n, int k, int skip, long long* idx, float* dist2, void* ws, const int** flags,
-                       cudaStream_t st) {
+                       const int** nflag_out, int* brute_n_max, cudaStream_t st) {
     const size_t bc = (size_t)b * c, bn = (size_t)b * n;
     unsigned char* p = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(ws) + 255) & ~(uintptr_t)255);
     float* mean = reinterpret_cast<float*>(p);
@@ -618,7 +615,9 @@ int knn_feat_tc_launch(const float* x, int b, int c, int n, int k, int skip, lon
     int* cand = reinterpret_cast<int*>(p);
     p += kf_align(bn * TF_CAP * 4);
     int* cnt = reinterpret_cast<int*>(p);
-    kf_mean_kernel<<<(unsigned)((bc + 7) / 8), 256, 0, st>>>(x, (int)bc, n, mean);
+    p += kf_align(bn * 4);
+    int* nflag = reinterpret_cast<int*>(p);
+    kf_mean_kernel<<<(unsigned)((bc + 7) / 8), 256, 0, st>>>(x, (int)bc, n, mean, nflag);
     PDGN_CHECK_LAUNCH();
     const int cps = (((c + 31) / 32 + KF_SLABS - 1) / KF_SLABS) * 32;   // channels per slab
     kf_prep_kernel<<<dim3((n + 31) / 32, b, KF_SLABS), 256, 0, st>>>(x, mean, c, n, cps, xc, xT, nrm);
@@ -639,23 +638,19 @@ int knn_feat_tc_launch(const float* x, int b, int c, int n, int k, int skip, lon
     if (tune_env("PDGN_KNN_FEAT_NOEPI")) idesc |= 2u;
     if (tnsel == 256) {
         PDGN_CUDA(cudaFuncSetAttribute(knn_feat_tc_kernel<256>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        knn_feat_tc_kernel<256><<<dim3(n / TF_M, b), TF_T, smem, st>>>(xc, nrm, c, n, k + skip, cand, cnt, nst, dbg, idesc);
+        knn_feat_tc_kernel<256><<<dim3(n / TF_M, b), TF_T, smem, st>>>(xc, nrm, c, n, k + skip, cand, cnt, nflag, nst, dbg, idesc);
     } else {
         PDGN_CUDA(cudaFuncSetAttribute(knn_feat_tc_kernel<128>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        knn_feat_tc_kernel<128><<<dim3(n / TF_M, b), TF_T, smem, st>>>(xc, nrm, c, n, k + skip, cand, cnt, nst, dbg, idesc);
+        knn_feat_tc_kernel<128><<<dim3(n / TF_M, b), TF_T, smem, st>>>(xc, nrm, c, n, k + skip, cand, cnt, nflag, nst, dbg, idesc);
     }
     PDGN_CHECK_LAUNCH();
     const size_t rr_smem = (size_t)8 * 33 * RR_RS * 4;
     PDGN_CUDA(cudaFuncSetAttribute(knn_feat_rerank_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)rr_smem));
-    knn_feat_rerank_kernel<<<(unsigned)((bn + 7) / 8), 256, rr_smem, st>>>(xT, cand, cnt, c, n, k, skip, (int)bn, idx, dist2);
+    knn_feat_rerank_kernel<<<(unsigned)((bn + 7) / 8), 256, rr_smem, st>>>(xT, cand, cnt, nflag, c, n, k, skip, (int)bn, idx, dist2);
     PDGN_CHECK_LAUNCH();
-    if (n > 33 * RR_RS) {                                            // larger clouds: the flagged queries in their own launch
-        const size_t bf_smem = (size_t)8 * n * 4;
-        PDGN_CUDA(cudaFuncSetAttribute(knn_feat_brute_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bf_smem));
-        knn_feat_brute_kernel<<<(unsigned)((bn + 7) / 8), 256, bf_smem, st>>>(xT, cnt, c, n, k, skip, (int)bn, idx, dist2);
-        PDGN_CHECK_LAUNCH();
-    }
-    *flags = nullptr;                                                // nothing left for the caller to recompute
+    *flags = cnt;                                                    // the caller's exact kernel takes the flagged queries the
+    *nflag_out = nflag;                                              //   re-rank kernel left (many of them, or a large cloud)
+    *brute_n_max = 33 * RR_RS;
     return PDGN_OK;
 }
 

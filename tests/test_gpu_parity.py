@@ -1098,3 +1098,24 @@ def test_knn_feat_tensor_core_path_edge_cases(dev, case):
     ridx, rd2 = ocpu.knn_feat(x, k, skip=skip)
     np.testing.assert_array_equal(C(idx), ridx)
     np.testing.assert_array_equal(C(d2), rd2)
+
+
+def test_knn_feat_tensor_core_path_many_flagged_queries(dev):
+    """A collapsed cloud (a few hundred distinct feature vectors repeated: every query sees more exact ties than its list holds) flags
+    thousands of queries: beyond KF_BRUTE_MAX the exact 64-query SIMT CTAs recompute them instead of one warp per query; a mildly
+    degenerate cloud (a handful of flagged queries) stays on the warp-level brute force.  Both must equal the oracle."""
+    from oracle import cpu as ocpu
+    from pdgn_b200 import ops
+    rng = np.random.default_rng(5)
+    base = rng.standard_normal((2, 32, 16)).astype(np.float32)
+    x = np.repeat(base, 64, axis=2)                                    # 1024 points, 16 distinct: 64-fold duplicates
+    idx, d2 = ops.knn_feat(G(x, dev), 10, skip=1, return_dist=True)
+    ridx, rd2 = ocpu.knn_feat(x, 10, skip=1)
+    np.testing.assert_array_equal(C(idx), ridx)
+    np.testing.assert_array_equal(C(d2), rd2)
+    y = rng.standard_normal((2, 32, 512)).astype(np.float32)
+    y[0, :, :80] = y[0, :, :1]                                         # one 80-fold duplicate: its 80 queries overflow a 64-entry list
+    idx, d2 = ops.knn_feat(G(y, dev), 10, skip=1, return_dist=True)
+    ridx, rd2 = ocpu.knn_feat(y, 10, skip=1)
+    np.testing.assert_array_equal(C(idx), ridx)
+    np.testing.assert_array_equal(C(d2), rd2)
