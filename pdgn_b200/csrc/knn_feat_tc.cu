@@ -12,22 +12,23 @@
 //           operand stage is one contiguous bulk copy; squared norms of the rounded rows; xT = x transposed [B,N,C] for the
 //           re-rank.  Distances are shift invariant: centring shrinks the norms to the spread of the features, and values that
 //           ARE tf32 make the tensor core's operand truncation a no-op.
-//   filter  (knn_feat_tc_kernel<128|256>)  CTA = 128 queries (= the 128 TMEM lanes) x all candidates; 5 warps.  Thread 128
+//   filter  (knn_feat_tc_kernel<128|256>)  CTA = 128 queries (= the 128 TMEM lanes) x all candidates; 9 warps.  Thread 256
 //           copies (cp.async.bulk into a ring of stages, "full" mbarriers) and issues tcgen05.mma.kind::tf32 (M = 128,
 //           N = 128 or 256, K = 8) for every 8 channels; tcgen05.commit releases the stage and hands a finished accumulator to
 //           the epilogue; two accumulators in TMEM, so the K loop of the next tile runs under the epilogue of this one.  Warps
-//           0-3 (thread = query) read their row back with tcgen05.ld:
+//           0-7 read accumulators with tcgen05.ld, two threads per query (every other 32-column chunk = disjoint subgroups):
 //             pass A  h = |xi|^2 + |xj|^2 - 2 G as running minima of 128 STRIDED subgroups (candidate j -> subgroup j mod 128)
 //                     in registers; bound = k'-th smallest of the 64 group minima (selnet.cuh, the xyz kernel's network);
 //             pass B  the Gram tiles are computed AGAIN (the tensor-core time is small next to the operand traffic) and every
-//                     candidate with h <= F is appended to the query's list (<= 32 entries).
+//                     candidate with h <= F is appended to the query's list in global memory (<= 64 entries).
 //           The margins are rigorous (kf_flag_threshold): U bounds the k'-th smallest REFERENCE distance from above and every
 //           candidate with d_ref <= U has h <= F.  Nothing depends on the tensor core's internal summation order beyond a
 //           generous absolute error term.
 //   rank    (knn_feat_rerank_kernel)  warp = query, lane = candidate: the exact reference chain over rows fetched coalesced into
-//           shared memory, rank by counting over the (d2, index) keys, ranks skip..skip+k-1 stored.
+//           shared memory, rank by counting over the (d2, index) keys, ranks skip..skip+k-1 stored; entries 32..63 in a second pass.
 //   Queries whose list overflowed, or that saw fewer than k' finite group minima (duplicates, clusters, NaN), are flagged and
-//   recomputed by knn_feat_brute_kernel (warp = query, all n exact distances, repeated minimum search).
+//   counted: up to KF_BRUTE_MAX of them are recomputed inside the re-rank kernel (kf_brute_query: warp = query, all n exact
+//   distances, repeated minimum search), more than that (collapsed clouds) by knn_feat.cu's exact 64-query CTAs.
 // Bring-up history and measurements: profiles/r02_knn_feat_tc.txt.
 #include "common.cuh"
 #include "selnet.cuh"
