@@ -437,7 +437,6 @@ static int kq_launch_ss(const float* xyz, const float* new_xyz, int b, int n, in
 int knn_gram_launch(const float* xyz, const float* new_xyz, int b, int n, int m, int k, int* idx, float* dist2, cudaStream_t st) {
     static const char* shape = tune_env("PDGN_KNN_GRAM_SHAPE");   // tuning hook: "4x4" = 4 warps x 4 queries per lane instead of 8 x 2
     if (shape && shape[0] == '4') return kq_launch_ss<4, 4>(xyz, new_xyz, b, n, m, k, idx, dist2, st);
-    if (shape && shape[0] == '1') return kq_launch_ss<16, 1>(xyz, new_xyz, b, n, m, k, idx, dist2, st);
     return kq_launch_ss<8, 2>(xyz, new_xyz, b, n, m, k, idx, dist2, st);
 }
 
