@@ -84,6 +84,9 @@ __device__ void kq_exact_query(const float* __restrict__ X, const float* __restr
                                float qx, float qy, float qz, int lane, unsigned long long* __restrict__ stage,
                                int* __restrict__ oi, float* __restrict__ od) {
     constexpr int PER = KQ_NSUB * SS / 32;
+    // staged as 4-byte distances (+inf = not a candidate), the index is the position: 8 KB for a full tile, which also fits the
+    // single 11.5 KB block a warp owns in the 16 x 1 shape
+    float* dst = reinterpret_cast<float*>(stage);
 #pragma unroll 4
     for (int i = 0; i < PER; ++i) {
         const int pos = lane + 32 * i;
@@ -91,14 +94,16 @@ __device__ void kq_exact_query(const float* __restrict__ X, const float* __restr
         const int pp = kq_pad(pos);
         const float d = d2_xyz(qx, qy, qz, X[pp], Y[pp], Z[pp]);
         const bool ok = j < n && d <= 3.402823466e+38f;                           // NaN / +inf are never selected
-        stage[i * 32 + lane] = ok ? (((unsigned long long)__float_as_uint(d) << 32) | (unsigned)j) : ~0ull;
+        dst[i * 32 + lane] = ok ? d : kInf;
     }
     unsigned long long last = 0;
     for (int e = 0; e < k; ++e) {
         unsigned long long best = ~0ull;
 #pragma unroll 4
         for (int i = 0; i < PER; ++i) {
-            const unsigned long long key = stage[i * 32 + lane];
+            const int pos = lane + 32 * i;
+            const float d = dst[i * 32 + lane];
+            const unsigned long long key = d < kInf ? (((unsigned long long)__float_as_uint(d) << 32) | (unsigned)((pos % SS) * KQ_NSUB + pos / SS)) : ~0ull;
             if ((e == 0 || key > last) && key < best) best = key;
         }
 #pragma unroll
@@ -437,6 +442,7 @@ static int kq_launch_ss(const float* xyz, const float* new_xyz, int b, int n, in
 int knn_gram_launch(const float* xyz, const float* new_xyz, int b, int n, int m, int k, int* idx, float* dist2, cudaStream_t st) {
     static const char* shape = tune_env("PDGN_KNN_GRAM_SHAPE");   // tuning hook: "4x4" = 4 warps x 4 queries per lane instead of 8 x 2
     if (shape && shape[0] == '4') return kq_launch_ss<4, 4>(xyz, new_xyz, b, n, m, k, idx, dist2, st);
+    if (shape && shape[0] == '1') return kq_launch_ss<16, 1>(xyz, new_xyz, b, n, m, k, idx, dist2, st);   // 16 warps x 1 query per lane
     return kq_launch_ss<8, 2>(xyz, new_xyz, b, n, m, k, idx, dist2, st);
 }
 
