@@ -52,22 +52,27 @@ __global__ void lp_transpose_add_kernel(const float* __restrict__ g, int n, floa
     d[j] += s[0]; d[n + j] += s[1]; d[2 * (size_t)n + j] += s[2];
 }
 
-// out[0] = (sum a0 + sum a1) / m, out[1] = (sum a2 + sum a3) / m; one CTA, fixed summation order (deterministic)
+// out[0] = (sum a0 + sum a1) / m, out[1] = (sum a2 + sum a3) / m; one CTA per output, fixed summation order (deterministic).
+// Four independent partial sums per thread keep 8 loads in flight (the arrays are L2 resident: the loop is latency bound).
 __global__ void __launch_bounds__(1024) lp_sums_kernel(const float* __restrict__ a0, const float* __restrict__ a1, const float* __restrict__ a2,
                                                       const float* __restrict__ a3, size_t count, float inv_m, float* __restrict__ out) {
-    __shared__ float red[2][32];
-    float s0 = 0.f, s1 = 0.f;
-    for (size_t i = threadIdx.x; i < count; i += 1024) {
-        s0 += a0[i] + a1[i];
-        s1 += a2[i] + a3[i];
+    __shared__ float red[32];
+    const float* p = blockIdx.x == 0 ? a0 : a2;
+    const float* q = blockIdx.x == 0 ? a1 : a3;
+    float s[4] = {0.f, 0.f, 0.f, 0.f};
+    size_t i = threadIdx.x;
+    for (; i + 3 * 1024 < count; i += 4 * 1024) {
+#pragma unroll
+        for (int u = 0; u < 4; ++u) s[u] += p[i + u * 1024] + q[i + u * 1024];
     }
-    s0 = warp_sum(s0); s1 = warp_sum(s1);
+    for (; i < count; i += 1024) s[0] += p[i] + q[i];
+    float t = warp_sum((s[0] + s[1]) + (s[2] + s[3]));
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    if (lane == 0) { red[0][warp] = s0; red[1][warp] = s1; }
+    if (lane == 0) red[warp] = t;
     __syncthreads();
     if (warp == 0) {
-        s0 = warp_sum(red[0][lane]); s1 = warp_sum(red[1][lane]);
-        if (lane == 0) { out[0] = s0 * inv_m; out[1] = s1 * inv_m; }
+        t = warp_sum(red[lane]);
+        if (lane == 0) out[blockIdx.x] = t * inv_m;
     }
 }
 
@@ -118,7 +123,7 @@ extern "C" int pdgn_local_pair_fwd(const float* pt1, const float* pt2, int b, in
     // ChamferLoss(preds = stats of pt2, gts = stats of pt1): both directional minima (chamfer_loss.py:13-20)
     PDGN_LP_TRY(pdgn_chamfer_min(W + L.mu2, W + L.mu1, b, m, m, 3, W + L.mn[0], WI + L.mn[1], W + L.mn[2], WI + L.mn[3], stream));
     PDGN_LP_TRY(pdgn_chamfer_min(W + L.cov2, W + L.cov1, b, m, m, 6, W + L.mn[4], WI + L.mn[5], W + L.mn[6], WI + L.mn[7], stream));
-    lp_sums_kernel<<<1, 1024, 0, st>>>(W + L.mn[0], W + L.mn[2], W + L.mn[4], W + L.mn[6], (size_t)b * m, 1.0f / (float)m, out);
+    lp_sums_kernel<<<2, 1024, 0, st>>>(W + L.mn[0], W + L.mn[2], W + L.mn[4], W + L.mn[6], (size_t)b * m, 1.0f / (float)m, out);
     PDGN_CHECK_LAUNCH();
     return PDGN_OK;
 }
