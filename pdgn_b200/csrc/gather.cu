@@ -464,6 +464,55 @@ __global__ void __launch_bounds__(GT) edge_fwd_kernel(const float* __restrict__ 
     }
 }
 
+// Shared-memory staged form (C >= 8), like group_fwd_smem_kernel: the cc feature rows of one (batch, channel chunk) sit in shared
+// memory, so the random neighbour gathers and the per-point centre reads are 32-bank LDS instead of L1/L2 gathers, and the two
+// [B,2C,N,k] halves stream out as 16-byte stores.  Index loads (int64, 32 bytes per thread) are software-pipelined.
+__global__ void __launch_bounds__(GT) edge_fwd_smem_kernel(const float* __restrict__ x, const long long* __restrict__ idx, int c, int n,
+                                                          int k, int cc_max, int jpart, float* __restrict__ ee) {
+    extern __shared__ __align__(16) float rows[];  // [cc][n]
+    const int bz = blockIdx.z;
+    const int c0 = blockIdx.y * cc_max, cc = min(cc_max, c - c0);
+    const int nk = n * k;
+    const float* src = x + ((size_t)bz * c + c0) * n;
+    if (((cc * n) & 3) == 0 && (reinterpret_cast<uintptr_t>(src) & 15) == 0) {
+        for (int e = threadIdx.x; e < (cc * n) >> 2; e += GT) reinterpret_cast<float4*>(rows)[e] = __ldg(reinterpret_cast<const float4*>(src) + e);
+    } else {
+        for (int e = threadIdx.x; e < cc * n; e += GT) rows[e] = __ldg(src + e);
+    }
+    __syncthreads();
+    const long long e_end = min((long long)nk, (long long)(blockIdx.x + 1) * jpart);
+    const long long* ip = idx + (size_t)bz * nk;
+    float* d0b = ee + ((size_t)bz * 2 * c + c0) * nk;          // central half
+    float* d1b = d0b + (size_t)c * nk;                          // neighbour - central half
+    long long e = (long long)blockIdx.x * jpart + threadIdx.x * 4;
+    longlong2 ia = make_longlong2(0, 0), ib = make_longlong2(0, 0);
+    if (e < e_end) {
+        ia = *reinterpret_cast<const longlong2*>(ip + e);
+        ib = *reinterpret_cast<const longlong2*>(ip + e + 2);
+    }
+    for (; e < e_end; e += GT * 4) {
+        const long long en = e + GT * 4;
+        longlong2 na = make_longlong2(0, 0), nb2 = make_longlong2(0, 0);
+        if (en < e_end) {
+            na = *reinterpret_cast<const longlong2*>(ip + en);
+            nb2 = *reinterpret_cast<const longlong2*>(ip + en + 2);
+        }
+        const int nb0 = (int)ia.x, nb1 = (int)ia.y, nb2i = (int)ib.x, nb3 = (int)ib.y;
+        const int ce0 = (int)(e / k), ce1 = (int)((e + 1) / k), ce2 = (int)((e + 2) / k), ce3 = (int)((e + 3) / k);
+        const float* r = rows;
+        float* d0 = d0b + e;
+        float* d1 = d1b + e;
+#pragma unroll 4
+        for (int ch = 0; ch < cc; ++ch, r += n, d0 += nk, d1 += nk) {
+            const float a0 = r[ce0], a1 = r[ce1], a2 = r[ce2], a3 = r[ce3];
+            st_stream4(d0, make_float4(a0, a1, a2, a3));
+            st_stream4(d1, make_float4(__fsub_rn(r[nb0], a0), __fsub_rn(r[nb1], a1), __fsub_rn(r[nb2i], a2), __fsub_rn(r[nb3], a3)));
+        }
+        ia = na;
+        ib = nb2;
+    }
+}
+
 // grad_x[b,ch,i] += sum_s (g_central[i,s] - g_nbr[i,s]) ;  grad_x[b,ch,idx[i,s]] += g_nbr[i,s]
 __global__ void __launch_bounds__(GT) edge_bwd_kernel(const float* __restrict__ grad_ee, const long long* __restrict__ idx, int c,
                                                      int n, int k, int cpb, float* __restrict__ grad_x) {
@@ -812,12 +861,36 @@ extern "C" int pdgn_edge_feat_fwd(const float* x, const int64_t* idx, int b, int
     PDGN_VERIFY_IDX64(idx, (size_t)b * n * k, n, (cudaStream_t)stream);
     if (b > 65535 || nk > 0x7fffffffLL) return PDGN_ERR_UNSUPPORTED;
     const bool vec = (nk % 4 == 0) && (reinterpret_cast<uintptr_t>(ee) % 16 == 0);
+    const long long* ip = reinterpret_cast<const long long*>(idx);
+    // measured (tools/edge_fwd_time.py, B=35, k=10): C=256 N=1024 167 -> 143 us (5.4 TB/s); the generator's small stages are launch-
+    // latency sized and stay on the plain kernel
+    if (vec && c >= 8 && (long long)c * n >= 131072 && (size_t)n * 4 * 4 <= GS_ROW_BYTES && (reinterpret_cast<uintptr_t>(idx) % 16 == 0)) {
+        // shared-memory staged path (same plan as pdgn_group_fwd): cc rows of n floats per CTA, positions split into parts
+        int cc = 4;
+        while (cc * 2 <= c && (size_t)cc * 2 * n * 4 <= GS_ROW_BYTES) cc *= 2;
+        const int chunks = (c + cc - 1) / cc;
+        long long parts = (4LL * 148 * 3 + (long long)chunks * b - 1) / ((long long)chunks * b);
+        const long long max_parts = (nk + GT * 4 - 1) / (GT * 4);
+        if (parts > max_parts) parts = max_parts;
+        if (parts < 1) parts = 1;
+        long long jpart = (nk + parts - 1) / parts;
+        jpart = (jpart + GT * 4 - 1) / (GT * 4) * (GT * 4);
+        parts = (nk + jpart - 1) / jpart;
+        const size_t smem = (size_t)cc * n * 4;
+        dim3 sgrid((unsigned)parts, chunks, b);
+        static const char* ef_env = tune_env("PDGN_EDGE_FWD_IMPL");   // "plain": the unstaged kernel (A/B)
+        if (sgrid.y <= 65535 && !(ef_env && ef_env[0] == 'p')) {
+            PDGN_CUDA(cudaFuncSetAttribute(edge_fwd_smem_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+            edge_fwd_smem_kernel<<<sgrid, GT, smem, (cudaStream_t)stream>>>(x, ip, c, n, k, cc, (int)jpart, ee);
+            PDGN_CHECK_LAUNCH();
+            return PDGN_OK;
+        }
+    }
     const long long per = vec ? 4 : 1;
     const unsigned gx = (unsigned)((nk + GT * per - 1) / (GT * per));
     const int cpb = pick_cpb((long long)gx * b, c);
     dim3 grid(gx, (c + cpb - 1) / cpb, b);
     if (grid.y > 65535) return PDGN_ERR_UNSUPPORTED;
-    const long long* ip = reinterpret_cast<const long long*>(idx);
     if (vec) edge_fwd_kernel<true><<<grid, GT, 0, (cudaStream_t)stream>>>(x, ip, c, n, k, cpb, ee);
     else edge_fwd_kernel<false><<<grid, GT, 0, (cudaStream_t)stream>>>(x, ip, c, n, k, cpb, ee);
     PDGN_CHECK_LAUNCH();
