@@ -104,3 +104,19 @@ def test_modules_mirror_the_reference_names(built):
         assert hasattr(evaluation_metrics, name), name
     for name in ["get_edge_features", "get_edge_features_xyz"]:
         assert hasattr(edge_features, name), name
+
+
+def test_workspace_queries_need_no_gpu(built):
+    """The *_workspace entry points are pure host arithmetic (callable without a device): positive for sane shapes, growing with
+    the problem, 0 for nonsense; pdgn_knn_feat_workspace covers the tensor-core path's centred tiled copy (channels padded to 32),
+    the transposed copy, partial norms, 64-entry candidate lists and counters."""
+    from pdgn_b200 import _lib
+    L = _lib.lib()
+    small, big = L.pdgn_knn_feat_workspace(2, 40, 640), L.pdgn_knn_feat_workspace(35, 256, 1024)
+    assert 0 < small < big
+    n_pad = 2 * 64 * 640 * 4                      # centred copy: 40 channels padded to 64
+    assert small >= n_pad + 2 * 40 * 640 * 4 + 2 * 640 * 64 * 4
+    assert L.pdgn_knn_feat_workspace(-1, 8, 128) == 0
+    assert L.pdgn_group_bwd_workspace(35, 1024, 1024, 10) > 35 * 1024 * 10 * 4
+    assert L.pdgn_interp_bwd_workspace(35, 2048, 1024) > 35 * 2048 * 3 * 4
+    assert L.pdgn_edge_feat_bwd_workspace(35, 1024, 10) > 35 * 1024 * 10 * 4
