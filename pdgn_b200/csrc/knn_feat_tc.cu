@@ -160,15 +160,18 @@ __device__ __forceinline__ void kf_tmem_ld32(uint32_t taddr, float (&v)[32]) {
 // Bounds of one query.  ni = |xi|^2 and mx = max_j |xj|^2 of the centred, tf32-rounded rows; a16 = bf16 bits (rounded down) of
 // the k'-th smallest group minimum of h = ni + nj - 2 G.  With x~ the rounded rows and x^ = x - mean: |x~ - x^| <= 2^-11 |x^|
 // per component, so | |x~i - x~j| - |xi - xj| | <= eps = 2^-11 (|x^i| + |x^j|) <= 1.01 * 2^-11 (sqrt(ni) + sqrt(mx)), and the
-// computed h differs from |x~i - x~j|^2 by at most acc (rounding of the norms, of ni + nj - 2G, and whatever order the tensor
-// core sums its 22-bit-exact products in: 2^-17 (sqrt(ni) + sqrt(mx))^2 is > 100 FP32 ulps of the largest term).  The
-// reference chain's own rounding is dc = (c + 4) 2^-23 relative.  Hence
+// computed h differs from |x~i - x~j|^2 by at most acc.  The tensor core multiplies the 11-bit operands exactly (22-bit products)
+// and sums c of them in FP32 in an order and rounding mode we do not rely on: even truncating after every addition the sum is
+// within c 2^-23 sum|x~ic x~jc| <= c 2^-23 |x~i||x~j| of the exact one; h doubles that, and the norms (FP32 sums of c squares)
+// and the two final additions add a few ulps of ni + nj.  With s = |x~i| + max|x~j| (s^2 >= 4 |x~i||x~j|, s^2 >= ni + nj / 2):
+// acc = (c + 16) 2^-23 s^2 >= 2 (2 c 2^-23 |x~i||x~j|) + 16 2^-23 (ni + nj) / 2 -- twice the worst case.  The reference chain's
+// own rounding is dc = (c + 4) 2^-23 relative.  Hence
 //   U  = (sqrt(A + acc) + eps)^2 (1 + dc)        >= the k'-th smallest REFERENCE distance   (A = the bf16 bound, one ulp up)
 //   F  = (sqrt(U (1 + 2 dc)) + eps)^2 + acc      >= h of every candidate with d_ref <= U.
 __device__ __forceinline__ float kf_flag_threshold(unsigned a16, float ni, float mx, int c) {
     const float s = __fadd_ru(__fsqrt_ru(ni), __fsqrt_ru(mx));
     const float eps = __fmul_ru(s, 1.01f * 4.8828125e-4f);                 // 2^-11
-    const float acc = __fmul_ru(__fmul_ru(s, s), 7.62939453125e-6f);       // 2^-17
+    const float acc = __fmul_ru(__fmul_ru(s, s), (float)(c + 16) * 1.1920929e-7f);   // (c + 16) 2^-23 s^2
     const float dc = (float)(c + 4) * 1.1920929e-7f;                       // 2^-23
     const float a = __uint_as_float((a16 + 1u) << 16);
     float r = __fadd_ru(__fsqrt_ru(__fadd_ru(a, acc)), eps);
